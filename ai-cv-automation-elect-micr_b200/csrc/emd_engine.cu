@@ -1,0 +1,963 @@
+// emd_engine.cu -- the engine behind the C ABI of include/emd.h.
+//
+// The reference builds a TensorFlow graph (get_model_fn/_tower_fn/architecture, DEN:463-581,
+// DMG:200-540) and runs it with one sess.run per 512x512 crop (DEN:646-647).  Here the graph is a
+// static schedule of fused steps over NHWC activations in one workspace arena; a batch of crops
+// goes through every step together.  Nothing in this file computes on the CPU: if CUDA is not
+// usable every entry point fails with EMD_ECUDA.
+#include "../../include/emd.h"
+#include "emd_kernels.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace emd;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Tensor {
+  std::string name;
+  int H, W, C;
+  bool external;        // network input / output: lives in caller (or staging) memory, always f32
+  size_t offset = 0;    // bytes into the arena (image 0 of the batch)
+  size_t bytes = 0;     // bytes reserved (max_batch images, 4-byte elements)
+  int first = 1 << 30, last = -1;
+};
+
+struct Ref { int t = -1, coff = 0, C = 0; };
+
+enum StepKind { SK_DW, SK_CONV, SK_DECONV, SK_RESIZE, SK_POOL };
+
+struct Step {
+  StepKind kind;
+  std::string name;    // unique step name
+  std::string layer;   // reference layer this step belongs to (emd_run_layer group)
+  Ref in, out, res;
+  int Cin = 0, Cout = 0, k = 1, stride = 1, rate = 1;
+  bool relu6 = false, clip01 = false;
+  std::string wname;   // blob prefix
+  const float *w = nullptr, *scale = nullptr, *shift = nullptr, *dw = nullptr;
+  void* w16[3] = {nullptr, nullptr, nullptr};  // indexed by ElemType
+  float ms = 0.f;
+  double flops = 0, bytes = 0;  // per crop: algorithmic FLOPs and (16-bit storage) HBM bytes
+};
+
+struct BlobEntry { uint32_t rows, cols; size_t offset; };
+
+}  // namespace
+
+struct emd_engine {
+  int device = 0, S = 512, variant = 0, max_batch = 1, num_sms = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::vector<Tensor> tensors;
+  std::vector<Step> steps;
+  std::map<std::string, Ref> named;      // activation name -> view
+  int t_input = -1, t_output = -1;
+  bool keep = false, profile = false, weights_loaded = false, use_umma = true;
+  char* arena = nullptr; size_t arena_bytes = 0;
+  char* d_blob = nullptr; size_t blob_bytes = 0;
+  std::map<std::string, BlobEntry> entries;
+  std::vector<void*> w16_allocs;
+  long long launches = 0;
+  int last_n = 0, last_et = 0;
+  // staging for host I/O of emd_forward
+  float *d_stage_in = nullptr, *d_stage_out = nullptr;
+  // whole-image pipeline buffers (grown on demand)
+  void* d_img_raw = nullptr; size_t img_raw_bytes = 0;
+  float* d_img = nullptr; size_t img_bytes = 0;
+  float *d_crops = nullptr, *d_tiles = nullptr; size_t crops_bytes = 0;
+  double* d_sout = nullptr; size_t sout_bytes = 0;
+  double* d_minmax = nullptr; void* d_partial = nullptr;
+  int* d_origins = nullptr;  // ys then xs, 2*256 ints
+  std::vector<cudaEvent_t> events;
+};
+
+namespace {
+
+int fail(emd_engine* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (e) e->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU(e, call)                                                                         \
+  do {                                                                                      \
+    cudaError_t _r = (call);                                                                \
+    if (_r != cudaSuccess)                                                                  \
+      return fail(e, EMD_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_r), __FILE__, __LINE__); \
+  } while (0)
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---------------------------------------------------------------------------------------------
+// schedule construction (variant A: DMG:392-540)
+// ---------------------------------------------------------------------------------------------
+struct Builder {
+  emd_engine* e;
+  int add_tensor(const std::string& name, int H, int W, int C, bool external = false) {
+    Tensor t; t.name = name; t.H = H; t.W = W; t.C = C; t.external = external;
+    e->tensors.push_back(t);
+    int id = (int)e->tensors.size() - 1;
+    e->named[name] = Ref{id, 0, C};
+    return id;
+  }
+  Ref whole(int t) { return Ref{t, 0, e->tensors[t].C}; }
+  Ref slice(int t, int coff, int C, const std::string& alias) {
+    Ref r{t, coff, C};
+    if (!alias.empty()) e->named[alias] = r;
+    return r;
+  }
+  // strided_conv_block (DMG:250-276): depthwise 3x3 (stride, rate) -> pointwise + folded BNx2 + ReLU6 (+ residual)
+  void sep(const std::string& name, Ref in, Ref out, int Cin, int Cout, int stride, int rate, Ref res = Ref()) {
+    const Tensor& ti = e->tensors[in.t];
+    int OH = (ti.H + stride - 1) / stride, OW = (ti.W + stride - 1) / stride;
+    int tmp = add_tensor(name + ":dw", OH, OW, Cin);
+    Step d; d.kind = SK_DW; d.name = name + ":dw"; d.layer = name; d.in = in; d.out = whole(tmp);
+    d.Cin = d.Cout = Cin; d.k = 3; d.stride = stride; d.rate = rate; d.wname = name;
+    e->steps.push_back(d);
+    Step c; c.kind = SK_CONV; c.name = name; c.layer = name; c.in = whole(tmp); c.out = out; c.res = res;
+    c.Cin = Cin; c.Cout = Cout; c.k = 1; c.relu6 = true; c.wname = name;
+    e->steps.push_back(c);
+  }
+  // conv_block_not_sep / residual_conv / ASPP convs: k x k conv + bias + folded BN + ReLU6
+  void conv(const std::string& name, Ref in, Ref out, int Cin, int Cout, int k, int stride, int rate, bool relu6,
+            Ref res = Ref(), bool clip01 = false, const std::string& layer = "") {
+    Step c; c.kind = SK_CONV; c.name = name; c.layer = layer.empty() ? name : layer; c.in = in; c.out = out; c.res = res;
+    c.Cin = Cin; c.Cout = Cout; c.k = k; c.stride = stride; c.rate = rate; c.relu6 = relu6; c.clip01 = clip01;
+    c.wname = name;
+    e->steps.push_back(c);
+  }
+  void deconv(const std::string& name, Ref in, Ref out, int Cin, int Cout) {  // deconv_block, DMG:278-289
+    Step c; c.kind = SK_DECONV; c.name = name; c.layer = name; c.in = in; c.out = out;
+    c.Cin = Cin; c.Cout = Cout; c.k = 3; c.stride = 2; c.relu6 = true; c.wname = name;
+    e->steps.push_back(c);
+  }
+};
+
+void build_schedule_A(emd_engine* e) {
+  Builder b{e};
+  const int S = e->S, f0 = 64, f1 = 128, f2 = 256, f3 = 728, f4 = 728, ao = 256;
+  e->t_input = b.add_tensor("input", S, S, 1, true);
+  e->t_output = b.add_tensor("output", S, S, 1, true);
+  const int concat1 = b.add_tensor("concat1", S / 2, S / 2, f2 + f1);   // [deconv2to1, cnn0_strided] DMG:509-511
+  const int concat2 = b.add_tensor("concat2", S / 4, S / 4, ao + f1);   // [upsampled aspp, cnn1_strided] DMG:497-499
+  const int cat5 = b.add_tensor("aspp_concat", S / 16, S / 16, 5 * f4);  // DMG:348-350
+  Ref in = b.whole(e->t_input);
+
+  // encoding blocks 0-3 (DMG:395-453): sep, sep, sep(stride 2) + 1x1 stride-2 residual, added after ReLU6
+  struct Enc { int cin, a, b, c; };
+  const Enc enc[4] = {{1, f0, f0, f1}, {f1, f1, f1, f1}, {f1, f2, f2, f2}, {f2, f3, f3, f3}};
+  Ref cur = in;
+  int size = S;
+  for (int i = 0; i < 4; ++i) {
+    const std::string n = "cnn" + std::to_string(i);
+    int ta = b.add_tensor(n, size, size, enc[i].a);
+    int tb = b.add_tensor(n + "_last", size, size, enc[i].b);
+    int tr = b.add_tensor("residual" + std::to_string(i), size / 2, size / 2, enc[i].c);
+    Ref out;
+    const std::string en = "enc" + std::to_string(i);
+    if (i == 0) out = b.slice(concat1, f2, f1, en);
+    else if (i == 1) out = b.slice(concat2, ao, f1, en);
+    else out = b.whole(b.add_tensor(en, size / 2, size / 2, enc[i].c));
+    b.sep(n, cur, b.whole(ta), enc[i].cin, enc[i].a, 1, 1);
+    b.sep(n + "_last", b.whole(ta), b.whole(tb), enc[i].a, enc[i].b, 1, 1);
+    b.conv("residual" + std::to_string(i), cur, b.whole(tr), enc[i].cin, enc[i].c, 1, 2, 1, true);
+    b.sep(n + "_strided", b.whole(tb), out, enc[i].b, enc[i].c, 2, 1, b.whole(tr));
+    cur = out;
+    size /= 2;
+  }
+  // encoding block 4 (DMG:455-466) and the 11 middle blocks (DMG:468-469 -> 375-390)
+  const int s16 = S / 16;
+  Ref trunk = cur;
+  for (int blk = -1; blk < 11; ++blk) {
+    const std::string base = blk < 0 ? std::string("cnn4_") : "mid" + std::to_string(blk) + "_";
+    int t0 = b.add_tensor(base + "0", s16, s16, f4);
+    int t1 = b.add_tensor(base + "1", s16, s16, f4);
+    int t2 = b.add_tensor(blk < 0 ? std::string("trunk4") : "trunk_mid" + std::to_string(blk), s16, s16, f4);
+    b.sep(base + "0", trunk, b.whole(t0), f4, f4, 1, 1);
+    b.sep(base + "1", b.whole(t0), b.whole(t1), f4, f4, 1, 1);
+    b.sep(base + "2", b.whole(t1), b.whole(t2), f4, f4, 1, 1, trunk);
+    trunk = b.whole(t2);
+  }
+  // ASPP (DMG:291-361): branches write straight into their slice of the 3640-channel concat
+  b.conv("aspp_1x1", trunk, b.slice(cat5, 0, f4, "aspp_1x1"), f4, f4, 1, 1, 1, true);
+  const int rates[3] = {6, 12, 18};
+  for (int i = 0; i < 3; ++i) {
+    const std::string n = "aspp_r" + std::to_string(rates[i]);
+    b.conv(n, trunk, b.slice(cat5, (i + 1) * f4, f4, n), f4, f4, 3, 1, rates[i], true);
+  }
+  {
+    int tp = b.add_tensor("aspp_pool", s16 / 2, s16 / 2, f4);
+    int ti = b.add_tensor("aspp_image_conv", s16 / 2, s16 / 2, f4);
+    Step p; p.kind = SK_POOL; p.name = "aspp_pool"; p.layer = "aspp_image"; p.in = trunk; p.out = b.whole(tp);
+    p.Cin = p.Cout = f4;
+    e->steps.push_back(p);
+    b.conv("aspp_image_conv", b.whole(tp), b.whole(ti), f4, f4, 1, 1, 1, false, Ref(), false, "aspp_image");
+    e->steps.back().wname = "aspp_image";
+    Step r; r.kind = SK_RESIZE; r.name = "aspp_image"; r.layer = "aspp_image"; r.in = b.whole(ti);
+    r.out = b.slice(cat5, 4 * f4, f4, "aspp_image"); r.Cin = r.Cout = f4; r.relu6 = true; r.wname = "aspp_image:post";
+    e->steps.push_back(r);
+  }
+  int taspp = b.add_tensor("aspp_pellet", s16, s16, ao);
+  b.conv("aspp_pellet", b.whole(cat5), b.whole(taspp), 5 * f4, ao, 1, 1, 1, true);
+  // decoder (DMG:494-531)
+  {
+    Step r; r.kind = SK_RESIZE; r.name = "upsample4"; r.layer = "upsample4"; r.in = b.whole(taspp);
+    r.out = b.slice(concat2, 0, ao, "upsample4"); r.Cin = r.Cout = ao;
+    e->steps.push_back(r);
+  }
+  struct Dec { const char* n; int cat; int cin, cout, size; };
+  int d2a = b.add_tensor("deconv2_0", S / 4, S / 4, f2), d2r = b.add_tensor("residual2_d", S / 4, S / 4, f2);
+  int dec2 = b.add_tensor("dec2", S / 4, S / 4, f2);
+  b.sep("deconv2_0", b.whole(concat2), b.whole(d2a), ao + f1, f2, 1, 1);
+  b.conv("residual2_d", b.whole(concat2), b.whole(d2r), ao + f1, f2, 1, 1, 1, true);
+  b.sep("deconv2_1", b.whole(d2a), b.whole(dec2), f2, f2, 1, 1, b.whole(d2r));
+  b.deconv("deconv2to1", b.whole(dec2), b.slice(concat1, 0, f2, "deconv2to1"), f2, f2);
+  int d1a = b.add_tensor("deconv1_0", S / 2, S / 2, f1), d1r = b.add_tensor("residual1_d", S / 2, S / 2, f1);
+  int dec1 = b.add_tensor("dec1", S / 2, S / 2, f1);
+  b.sep("deconv1_0", b.whole(concat1), b.whole(d1a), f2 + f1, f1, 1, 1);
+  b.conv("residual1_d", b.whole(concat1), b.whole(d1r), f2 + f1, f1, 1, 1, 1, true);
+  b.sep("deconv1_1", b.whole(d1a), b.whole(dec1), f1, f1, 1, 1, b.whole(d1r));
+  int d1to0 = b.add_tensor("deconv1to0", S, S, f1);
+  b.deconv("deconv1to0", b.whole(dec1), b.whole(d1to0), f1, f1);
+  int d0a = b.add_tensor("deconv0_0", S, S, f0), d0r = b.add_tensor("residual0_d", S, S, f0);
+  int dec0 = b.add_tensor("dec0", S, S, f0);
+  b.sep("deconv0_0", b.whole(d1to0), b.whole(d0a), f1, f0, 1, 1);
+  b.conv("residual0_d", b.whole(d1to0), b.whole(d0r), f1, f0, 1, 1, 1, true);
+  b.sep("deconv0_1", b.whole(d0a), b.whole(dec0), f0, f0, 1, 1, b.whole(d0r));
+  // final 3x3 conv -> BN -> ReLU6 (DMG:531) + in-graph clip (DMG:534-538), written as f32
+  b.conv("final", b.whole(dec0), b.whole(e->t_output), f0, 1, 3, 1, 1, true, Ref(), true);
+}
+
+// algorithmic work per crop of each step (16-bit storage), for roofline reporting
+void annotate_work(emd_engine* e) {
+  for (Step& s : e->steps) {
+    const Tensor& ti = e->tensors[s.in.t];
+    const Tensor& to = e->tensors[s.out.t];
+    const double ipx = (double)ti.H * ti.W, opx = (double)to.H * to.W;
+    const double in_b = ipx * s.in.C * (ti.external ? 4 : 2), out_b = opx * s.out.C * (to.external ? 4 : 2);
+    const double res_b = s.res.t >= 0 ? opx * s.res.C * 2 : 0;
+    switch (s.kind) {
+      case SK_DW: s.flops = 2.0 * 9 * opx * s.Cin; s.bytes = in_b + out_b; break;
+      case SK_CONV: {
+        double taps = 0;  // in-bounds taps summed over output pixels
+        const int half = s.k / 2;
+        for (int ky = -half; ky <= half; ++ky)
+          for (int kx = -half; kx <= half; ++kx) {
+            const int dy = ky * s.rate, dx = kx * s.rate;
+            const double vy = std::max(0, to.H - std::abs(dy)), vx = std::max(0, to.W - std::abs(dx));
+            taps += (s.stride == 1) ? vy * vx : opx;
+          }
+        s.flops = 2.0 * taps * s.Cin * s.Cout;
+        s.bytes = in_b / (s.stride * s.stride) + out_b + res_b + 2.0 * s.k * s.k * s.Cin * s.Cout / e->max_batch;
+        break;
+      }
+      case SK_DECONV:
+        s.flops = 2.0 * ipx * 9 * s.Cin * s.Cout;
+        s.bytes = in_b + out_b + 2.0 * 9 * s.Cin * s.Cout / e->max_batch;
+        break;
+      default: s.flops = 4.0 * opx * s.Cout; s.bytes = in_b + out_b; break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// arena: lifetime-aware placement, greedy by size
+// ---------------------------------------------------------------------------------------------
+int plan_arena(emd_engine* e) {
+  for (Tensor& t : e->tensors) { t.first = 1 << 30; t.last = -1; }
+  for (int i = 0; i < (int)e->steps.size(); ++i) {
+    const Step& s = e->steps[i];
+    for (int t : {s.in.t, s.out.t, s.res.t}) {
+      if (t < 0) continue;
+      e->tensors[t].first = std::min(e->tensors[t].first, i);
+      e->tensors[t].last = std::max(e->tensors[t].last, i);
+    }
+  }
+  std::vector<int> order;
+  for (int i = 0; i < (int)e->tensors.size(); ++i) {
+    Tensor& t = e->tensors[i];
+    if (t.external || t.last < 0) continue;
+    t.bytes = (((size_t)t.H * t.W * t.C * 4 * e->max_batch) + 1023) & ~(size_t)1023;
+    if (e->keep) { t.first = 0; t.last = 1 << 30; }
+    order.push_back(i);
+  }
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return e->tensors[a].bytes > e->tensors[b].bytes; });
+  std::vector<int> placed;
+  size_t total = 0;
+  for (int id : order) {
+    Tensor& t = e->tensors[id];
+    std::vector<std::pair<size_t, size_t>> busy;
+    for (int pid : placed) {
+      const Tensor& p = e->tensors[pid];
+      if (p.first <= t.last && t.first <= p.last) busy.push_back({p.offset, p.offset + p.bytes});
+    }
+    std::sort(busy.begin(), busy.end());
+    size_t off = 0;
+    for (auto& iv : busy) {
+      if (off + t.bytes <= iv.first) break;
+      off = std::max(off, iv.second);
+    }
+    t.offset = off;
+    total = std::max(total, off + t.bytes);
+    placed.push_back(id);
+  }
+  if (total > e->arena_bytes) {
+    if (e->arena) cudaFree(e->arena);
+    e->arena = nullptr; e->arena_bytes = 0;
+    cudaError_t r = cudaMalloc(&e->arena, total);
+    if (r != cudaSuccess) return fail(e, EMD_ENOMEM, "workspace of %.2f GB: %s", total / 1e9, cudaGetErrorString(r));
+    e->arena_bytes = total;
+  }
+  return EMD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------------------------
+struct BlobHeader { char magic[8]; uint32_t n_entries, variant, reserved[4]; };            // 32 bytes
+struct BlobRecord { char name[48]; uint32_t rows, cols; uint64_t offset; };               // 64 bytes
+
+const float* entry_ptr(emd_engine* e, const std::string& name, uint32_t rows, uint32_t cols, std::string* why) {
+  auto it = e->entries.find(name);
+  if (it == e->entries.end()) { *why = "missing blob entry " + name; return nullptr; }
+  if (it->second.rows != rows || it->second.cols != cols) {
+    char b[160];
+    snprintf(b, sizeof b, "blob entry %s is %ux%u, expected %ux%u", name.c_str(), it->second.rows, it->second.cols, rows, cols);
+    *why = b; return nullptr;
+  }
+  return reinterpret_cast<const float*>(e->d_blob + it->second.offset);
+}
+
+int bind_weights(emd_engine* e, const char* host_blob) {
+  std::string why;
+  for (Step& s : e->steps) {
+    switch (s.kind) {
+      case SK_DW:
+        if (!(s.dw = entry_ptr(e, s.wname + "/dw", 9, s.Cin, &why))) return fail(e, EMD_EINVAL, "%s", why.c_str());
+        break;
+      case SK_CONV:
+      case SK_DECONV: {
+        const uint32_t K = (uint32_t)(s.k * s.k * s.Cin);
+        if (!(s.w = entry_ptr(e, s.wname + "/w", K, s.Cout, &why)) ||
+            !(s.scale = entry_ptr(e, s.wname + "/scale", 1, s.Cout, &why)) ||
+            !(s.shift = entry_ptr(e, s.wname + "/shift", 1, s.Cout, &why)))
+          return fail(e, EMD_EINVAL, "%s", why.c_str());
+        if (s.name == "aspp_image_conv") {  // conv + bias only; BN/ReLU6 come after the resize (DMG:338-345)
+          if (!(s.scale = entry_ptr(e, "aspp_image/one", 1, s.Cout, &why)) ||
+              !(s.shift = entry_ptr(e, "aspp_image/bias", 1, s.Cout, &why)))
+            return fail(e, EMD_EINVAL, "%s", why.c_str());
+        }
+        // 16-bit operand copies in the tcgen05 tile layout
+        const float* hw = reinterpret_cast<const float*>(host_blob + e->entries[s.wname + "/w"].offset);
+        for (int et : {ET_BF16, ET_F16}) {
+          size_t nb = umma_pack_weights(hw, s.k * s.k, s.Cin, s.Cout, et, nullptr);
+          if (!nb) continue;
+          std::vector<char> tmp(nb);
+          umma_pack_weights(hw, s.k * s.k, s.Cin, s.Cout, et, tmp.data());
+          void* d = nullptr;
+          CU(e, cudaMalloc(&d, nb));
+          e->w16_allocs.push_back(d);
+          CU(e, cudaMemcpy(d, tmp.data(), nb, cudaMemcpyHostToDevice));
+          s.w16[et] = d;
+        }
+        break;
+      }
+      case SK_RESIZE:
+        if (s.wname.empty()) break;
+        if (!(s.scale = entry_ptr(e, "aspp_image/scale", 1, s.Cout, &why)) ||
+            !(s.shift = entry_ptr(e, "aspp_image/bnshift", 1, s.Cout, &why)))
+          return fail(e, EMD_EINVAL, "%s", why.c_str());
+        break;
+      default: break;
+    }
+  }
+  return EMD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// execution
+// ---------------------------------------------------------------------------------------------
+struct Override { int t; void* ptr; };
+
+struct ExecCtx {
+  emd_engine* e;
+  int et, n;
+  cudaStream_t s;
+  const float* d_in;  // network input (device, f32)
+  float* d_out;       // network output (device, f32)
+  std::vector<Override> ov;
+};
+
+View make_view(const ExecCtx& c, Ref r) {
+  const Tensor& t = c.e->tensors[r.t];
+  View v; v.H = t.H; v.W = t.W; v.C = r.C;
+  for (const Override& o : c.ov)
+    if (o.t == r.t) { v.ptr = o.ptr; v.pitch = r.C; v.coff = 0; return v; }
+  v.pitch = t.C; v.coff = r.coff;
+  if (r.t == c.e->t_input) v.ptr = const_cast<float*>(c.d_in);
+  else if (r.t == c.e->t_output) v.ptr = c.d_out;
+  else v.ptr = c.e->arena + t.offset;
+  return v;
+}
+
+cudaError_t run_conv(ExecCtx& c, const ConvParams& p, int w16_ok) {
+  emd_engine* e = c.e;
+  if (c.et != ET_F32 && e->use_umma && w16_ok && umma_supported(p, c.et)) {
+    e->launches++;
+    return launch_conv_umma(p, c.et, e->num_sms, c.s);
+  }
+  e->launches++;
+  return launch_conv_simt(p, c.et, c.s);
+}
+
+cudaError_t run_step(ExecCtx& c, Step& s) {
+  emd_engine* e = c.e;
+  const Tensor& ti = e->tensors[s.in.t];
+  const Tensor& to = e->tensors[s.out.t];
+  switch (s.kind) {
+    case SK_DW: {
+      DwParams p{};
+      p.in = make_view(c, s.in); p.out = make_view(c, s.out);
+      p.N = c.n; p.OH = to.H; p.OW = to.W; p.stride = s.stride; p.rate = s.rate;
+      p.pad = (s.stride == 1) ? s.rate : 0;  // TF SAME: symmetric `rate` at stride 1; 0 before / 1 after at stride 2 on even sizes
+      p.w = s.dw; p.in_f32 = ti.external;
+      e->launches++;
+      return launch_dw3x3(p, c.et, c.s);
+    }
+    case SK_POOL: {
+      PoolParams p{}; p.in = make_view(c, s.in); p.out = make_view(c, s.out); p.N = c.n;
+      e->launches++;
+      return launch_avgpool(p, c.et, c.s);
+    }
+    case SK_RESIZE: {
+      ResizeParams p{}; p.in = make_view(c, s.in); p.out = make_view(c, s.out); p.N = c.n;
+      p.scale = s.scale; p.shift = s.shift; p.relu6 = s.relu6;
+      e->launches++;
+      return launch_resize(p, c.et, c.s);
+    }
+    case SK_CONV: {
+      ConvParams p{};
+      p.in = make_view(c, s.in); p.out = make_view(c, s.out);
+      if (s.res.t >= 0) p.res = make_view(c, s.res);
+      p.N = c.n; p.MH = to.H; p.MW = to.W;
+      p.istride = s.stride; p.ostride = 1; p.oy0 = p.ox0 = 0;
+      p.Cin = s.Cin; p.Cout = s.Cout; p.w = s.w; p.w16 = s.w16[c.et]; p.scale = s.scale; p.shift = s.shift;
+      p.relu6 = s.relu6; p.clip01 = s.clip01; p.out_f32 = to.external; p.in_f32 = ti.external;
+      // taps: TF SAME. stride 1: symmetric (k/2)*rate.  stride 2 only occurs with k = 1 here (DMG:365-370).
+      const int half = s.k / 2;
+      p.ntaps = 0;
+      for (int ky = 0; ky < s.k; ++ky)
+        for (int kx = 0; kx < s.k; ++kx) {
+          const int dy = (ky - half) * s.rate, dx = (kx - half) * s.rate;
+          if (std::abs(dy) >= ti.H || std::abs(dx) >= ti.W) continue;  // tap never in bounds (dilation >= map)
+          p.dy[p.ntaps] = dy; p.dx[p.ntaps] = dx; p.wrow[p.ntaps] = ky * s.k + kx; p.ntaps++;
+        }
+      return run_conv(c, p, s.w16[c.et] != nullptr);
+    }
+    case SK_DECONV: {
+      // conv2d_transpose 3x3 stride 2 SAME = 4 sub-pixel phases (App. A.4):
+      //   out[2j+0] = in[j] w[0] + in[j-1] w[2];  out[2j+1] = in[j] w[1]   (per axis)
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          ConvParams p{};
+          p.in = make_view(c, s.in); p.out = make_view(c, s.out);
+          p.N = c.n; p.MH = ti.H; p.MW = ti.W;
+          p.istride = 1; p.ostride = 2; p.oy0 = py; p.ox0 = px;
+          p.Cin = s.Cin; p.Cout = s.Cout; p.w = s.w; p.w16 = s.w16[c.et]; p.scale = s.scale; p.shift = s.shift;
+          p.relu6 = s.relu6;
+          const int kys[2][2] = {{0, 2}, {1, -1}}, dys[2][2] = {{0, -1}, {0, 0}};
+          p.ntaps = 0;
+          for (int a = 0; a < 2; ++a) {
+            if (kys[py][a] < 0) continue;
+            for (int b2 = 0; b2 < 2; ++b2) {
+              if (kys[px][b2] < 0) continue;
+              p.dy[p.ntaps] = dys[py][a]; p.dx[p.ntaps] = dys[px][b2];
+              p.wrow[p.ntaps] = kys[py][a] * 3 + kys[px][b2]; p.ntaps++;
+            }
+          }
+          cudaError_t r = run_conv(c, p, s.w16[c.et] != nullptr);
+          if (r != cudaSuccess) return r;
+        }
+      return cudaSuccess;
+    }
+  }
+  return cudaErrorInvalidValue;
+}
+
+int run_network(emd_engine* e, const float* d_in, float* d_out, int n, int mode, cudaStream_t s) {
+  ExecCtx c{e, mode == EMD_MODE_FP32 ? ET_F32 : (mode == EMD_MODE_BF16 ? ET_BF16 : ET_F16), n, s, d_in, d_out, {}};
+  if (e->profile && e->events.size() < e->steps.size() + 1) {
+    e->events.resize(e->steps.size() + 1);
+    for (auto& ev : e->events) CU(e, cudaEventCreate(&ev));
+  }
+  e->last_n = n; e->last_et = c.et;
+  for (size_t i = 0; i < e->steps.size(); ++i) {
+    if (e->profile) CU(e, cudaEventRecord(e->events[i], s));
+    cudaError_t r = run_step(c, e->steps[i]);
+    if (r != cudaSuccess) return fail(e, EMD_ECUDA, "step %s: %s", e->steps[i].name.c_str(), cudaGetErrorString(r));
+  }
+  if (e->profile) {
+    CU(e, cudaEventRecord(e->events[e->steps.size()], s));
+    CU(e, cudaStreamSynchronize(s));
+    for (size_t i = 0; i < e->steps.size(); ++i) cudaEventElapsedTime(&e->steps[i].ms, e->events[i], e->events[i + 1]);
+  }
+  return EMD_OK;
+}
+
+int check_mode(emd_engine* e, int mode) {
+  if (mode != EMD_MODE_FP32 && mode != EMD_MODE_BF16 && mode != EMD_MODE_FP16) return fail(e, EMD_EINVAL, "bad mode %d", mode);
+  if (!e->weights_loaded) return fail(e, EMD_ESTATE, "emd_load_weights has not been called");
+  return EMD_OK;
+}
+
+template <typename T>
+int grow(emd_engine* e, T** p, size_t* have, size_t need) {
+  if (*have >= need) return EMD_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *have = 0;
+  cudaError_t r = cudaMalloc(reinterpret_cast<void**>(p), need);
+  if (r != cudaSuccess) return fail(e, EMD_ENOMEM, "cudaMalloc(%zu): %s", need, cudaGetErrorString(r));
+  *have = need;
+  return EMD_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int emd_version(void) { return 100; }
+
+const char* emd_last_error(const emd_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int emd_create(emd_engine** out, int device, int cropsize, int variant, int max_batch) {
+  if (!out) return fail(nullptr, EMD_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (cropsize < 32 || cropsize % 32) return fail(nullptr, EMD_EINVAL, "cropsize %d: must be a multiple of 32 (>= 32)", cropsize);
+  if (variant != EMD_VARIANT_A) return fail(nullptr, EMD_EINVAL, "variant %d not built (only EMD_VARIANT_A)", variant);
+  if (max_batch < 1) return fail(nullptr, EMD_EINVAL, "max_batch %d", max_batch);
+  int ndev = 0;
+  cudaError_t r = cudaGetDeviceCount(&ndev);
+  if (r != cudaSuccess || ndev == 0)
+    return fail(nullptr, EMD_ECUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                r != cudaSuccess ? cudaGetErrorString(r) : "device count 0");
+  if (device < 0 || device >= ndev) return fail(nullptr, EMD_EINVAL, "device %d of %d", device, ndev);
+  emd_engine* e = new emd_engine();
+  e->device = device; e->S = cropsize; e->variant = variant; e->max_batch = max_batch;
+  const char* env = getenv("EMD_DISABLE_UMMA");
+  e->use_umma = !(env && env[0] == '1');
+#define CUC(call)                                                                                       \
+  do {                                                                                                  \
+    cudaError_t _r = (call);                                                                            \
+    if (_r != cudaSuccess) {                                                                            \
+      int code = fail(nullptr, EMD_ECUDA, "%s failed: %s", #call, cudaGetErrorString(_r));              \
+      emd_destroy(e);                                                                                   \
+      return code;                                                                                      \
+    }                                                                                                   \
+  } while (0)
+  CUC(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUC(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    int code = fail(nullptr, EMD_ECUDA, "device %d is sm_%d%d; this build is sm_100a only", device, prop.major, prop.minor);
+    emd_destroy(e);
+    return code;
+  }
+  e->num_sms = prop.multiProcessorCount;
+  CUC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  build_schedule_A(e);
+  annotate_work(e);
+  int rc = plan_arena(e);
+  if (rc != EMD_OK) { g_create_error = e->err; emd_destroy(e); return rc; }
+  const size_t io = (size_t)max_batch * cropsize * cropsize * sizeof(float);
+  CUC(cudaMalloc(&e->d_stage_in, io));
+  CUC(cudaMalloc(&e->d_stage_out, io));
+  CUC(cudaMalloc(&e->d_minmax, 2 * sizeof(double)));
+  CUC(cudaMalloc(&e->d_partial, minmax_partial_bytes()));
+  CUC(cudaMalloc(&e->d_origins, 512 * sizeof(int)));
+#undef CUC
+  *out = e;
+  return EMD_OK;
+}
+
+int emd_destroy(emd_engine* e) {
+  if (!e) return EMD_OK;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (void* p : e->w16_allocs) cudaFree(p);
+  for (void* p : {(void*)e->arena, (void*)e->d_blob, (void*)e->d_stage_in, (void*)e->d_stage_out, e->d_img_raw,
+                  (void*)e->d_img, (void*)e->d_crops, (void*)e->d_tiles, (void*)e->d_sout, (void*)e->d_minmax,
+                  e->d_partial, (void*)e->d_origins})
+    if (p) cudaFree(p);
+  for (auto ev : e->events) cudaEventDestroy(ev);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return EMD_OK;
+}
+
+int emd_load_weights(emd_engine* e, const void* blob, size_t nbytes) {
+  if (!e || !blob) return EMD_EINVAL;
+  CU(e, cudaSetDevice(e->device));
+  if (nbytes < sizeof(BlobHeader)) return fail(e, EMD_EINVAL, "blob too small");
+  const char* b = reinterpret_cast<const char*>(blob);
+  BlobHeader h; memcpy(&h, b, sizeof h);
+  if (memcmp(h.magic, "EMDW0001", 8) != 0) return fail(e, EMD_EINVAL, "bad blob magic");
+  if ((int)h.variant != e->variant) return fail(e, EMD_EINVAL, "blob is variant %u, engine is %d", h.variant, e->variant);
+  if (nbytes < sizeof h + (size_t)h.n_entries * sizeof(BlobRecord)) return fail(e, EMD_EINVAL, "blob truncated");
+  e->entries.clear();
+  for (uint32_t i = 0; i < h.n_entries; ++i) {
+    BlobRecord r; memcpy(&r, b + sizeof h + i * sizeof r, sizeof r);
+    r.name[47] = 0;
+    if (r.offset + (size_t)r.rows * r.cols * 4 > nbytes) return fail(e, EMD_EINVAL, "blob entry %s out of range", r.name);
+    e->entries[r.name] = BlobEntry{r.rows, r.cols, (size_t)r.offset};
+  }
+  if (e->d_blob) { cudaFree(e->d_blob); e->d_blob = nullptr; }
+  for (void* p : e->w16_allocs) cudaFree(p);
+  e->w16_allocs.clear();
+  CU(e, cudaMalloc(&e->d_blob, nbytes));
+  CU(e, cudaMemcpy(e->d_blob, blob, nbytes, cudaMemcpyHostToDevice));
+  e->blob_bytes = nbytes;
+  int rc = bind_weights(e, b);
+  if (rc != EMD_OK) return rc;
+  e->weights_loaded = true;
+  return EMD_OK;
+}
+
+int emd_forward(emd_engine* e, const float* crops, int n, float* out, int mode, void* stream) {
+  if (!e || !crops || !out || n < 0) return EMD_EINVAL;
+  int rc = check_mode(e, mode);
+  if (rc) return rc;
+  CU(e, cudaSetDevice(e->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  const bool in_dev = is_device_ptr(crops), out_dev = is_device_ptr(out);
+  const size_t per = (size_t)e->S * e->S;
+  for (int c0 = 0; c0 < n; c0 += e->max_batch) {
+    const int nb = std::min(e->max_batch, n - c0);
+    const float* d_in = crops + c0 * per;
+    float* d_out = out + c0 * per;
+    if (!in_dev) {
+      CU(e, cudaMemcpyAsync(e->d_stage_in, d_in, nb * per * 4, cudaMemcpyHostToDevice, s));
+      d_in = e->d_stage_in;
+    }
+    if (!out_dev) d_out = e->d_stage_out;
+    rc = run_network(e, d_in, d_out, nb, mode, s);
+    if (rc) return rc;
+    if (!out_dev) CU(e, cudaMemcpyAsync(out + c0 * per, d_out, nb * per * 4, cudaMemcpyDeviceToHost, s));
+  }
+  if (!out_dev || !in_dev) CU(e, cudaStreamSynchronize(s));
+  return EMD_OK;
+}
+
+int emd_plan_tiles(int H, int W, int crop, int overlap, int* ys, int* xs, int* ny, int* nx) {
+  if (!ys || !xs || !ny || !nx || crop <= 0 || overlap < 0 || overlap >= crop || H < crop || W < crop) return EMD_EINVAL;
+  const int sizes[2] = {H, W};
+  int* outs[2] = {ys, xs};
+  int* counts[2] = {ny, nx};
+  for (int a = 0; a < 2; ++a) {
+    const int num = sizes[a] / (crop - overlap) + 1;          // DEN:661-662
+    const double len = (double)sizes[a] / (double)num;         // DEN:663-664 (true division)
+    for (int i = 0; i < num; ++i) {
+      int o = (int)std::nearbyint((double)i * len);            // np.round: half-to-even (App. D-2)
+      outs[a][i] = std::min(o, sizes[a] - crop);               // clamp (App. D-3)
+    }
+    *counts[a] = num;
+  }
+  return EMD_OK;
+}
+
+int emd_normalise(emd_engine* e, const void* img, int in_f64, int H, int W, float* out, void* stream) {
+  if (!e || !img || !out || H <= 0 || W <= 0) return EMD_EINVAL;
+  CU(e, cudaSetDevice(e->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  const size_t n = (size_t)H * W, esz = in_f64 ? 8 : 4;
+  const bool in_dev = is_device_ptr(img), out_dev = is_device_ptr(out);
+  const void* d_src = img;
+  if (!in_dev) {
+    int rc = grow(e, reinterpret_cast<char**>(&e->d_img_raw), &e->img_raw_bytes, n * esz);
+    if (rc) return rc;
+    CU(e, cudaMemcpyAsync(e->d_img_raw, img, n * esz, cudaMemcpyHostToDevice, s));
+    d_src = e->d_img_raw;
+  }
+  float* d_dst = out;
+  if (!out_dev) {
+    int rc = grow(e, &e->d_img, &e->img_bytes, n * 4);
+    if (rc) return rc;
+    d_dst = e->d_img;
+  }
+  CU(e, launch_minmax(d_src, in_f64, n, e->d_minmax, e->d_partial, s));
+  CU(e, launch_normalise_apply(d_src, in_f64, n, e->d_minmax, d_dst, s));
+  e->launches += 3;
+  if (!out_dev) {
+    CU(e, cudaMemcpyAsync(out, d_dst, n * 4, cudaMemcpyDeviceToHost, s));
+    CU(e, cudaStreamSynchronize(s));
+  }
+  return EMD_OK;
+}
+
+static int upload_origins(emd_engine* e, const int* ys, const int* xs, int ny, int nx, cudaStream_t s) {
+  if (ny < 1 || nx < 1 || ny > 256 || nx > 256) return fail(e, EMD_EINVAL, "tile grid %dx%d", ny, nx);
+  CU(e, cudaMemcpyAsync(e->d_origins, ys, ny * sizeof(int), cudaMemcpyHostToDevice, s));
+  CU(e, cudaMemcpyAsync(e->d_origins + 256, xs, nx * sizeof(int), cudaMemcpyHostToDevice, s));
+  return EMD_OK;
+}
+
+int emd_gather_crops(emd_engine* e, const float* img, int H, int W, const int* ys, const int* xs, int ny, int nx,
+                     int crop, float* crops, void* stream) {
+  if (!e || !img || !ys || !xs || !crops || crop % 4) return EMD_EINVAL;
+  CU(e, cudaSetDevice(e->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  int rc = upload_origins(e, ys, xs, ny, nx, s);
+  if (rc) return rc;
+  const size_t nimg = (size_t)H * W * 4, ncr = (size_t)ny * nx * crop * crop * 4;
+  const bool in_dev = is_device_ptr(img), out_dev = is_device_ptr(crops);
+  const float* d_src = img;
+  if (!in_dev) {
+    if ((rc = grow(e, &e->d_img, &e->img_bytes, nimg))) return rc;
+    CU(e, cudaMemcpyAsync(e->d_img, img, nimg, cudaMemcpyHostToDevice, s));
+    d_src = e->d_img;
+  }
+  float* d_dst = crops;
+  if (!out_dev) {
+    if ((rc = grow(e, &e->d_crops, &e->crops_bytes, ncr))) return rc;
+    d_dst = e->d_crops;
+  }
+  CU(e, launch_gather(d_src, H, W, e->d_origins, e->d_origins + 256, ny, nx, crop, d_dst, s));
+  e->launches++;
+  if (!out_dev) {
+    CU(e, cudaMemcpyAsync(crops, d_dst, ncr, cudaMemcpyDeviceToHost, s));
+    CU(e, cudaStreamSynchronize(s));
+  }
+  return EMD_OK;
+}
+
+int emd_stitch(emd_engine* e, const float* tiles, const int* ys, const int* xs, int ny, int nx, int crop, int H, int W,
+               int clip, double* out, void* stream) {
+  if (!e || !tiles || !ys || !xs || !out) return EMD_EINVAL;
+  CU(e, cudaSetDevice(e->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  int rc = upload_origins(e, ys, xs, ny, nx, s);
+  if (rc) return rc;
+  const size_t ntl = (size_t)ny * nx * crop * crop * 4, nout = (size_t)H * W * 8;
+  const bool in_dev = is_device_ptr(tiles), out_dev = is_device_ptr(out);
+  const float* d_src = tiles;
+  if (!in_dev) {
+    size_t have = e->crops_bytes;
+    if ((rc = grow(e, &e->d_tiles, &have, ntl))) return rc;
+    // d_tiles shares the size bookkeeping of d_crops only when both were grown together; keep it simple:
+    CU(e, cudaMemcpyAsync(e->d_tiles, tiles, ntl, cudaMemcpyHostToDevice, s));
+    d_src = e->d_tiles;
+  }
+  double* d_dst = out;
+  if (!out_dev) {
+    if ((rc = grow(e, &e->d_sout, &e->sout_bytes, nout))) return rc;
+    d_dst = e->d_sout;
+  }
+  CU(e, launch_stitch(d_src, e->d_origins, e->d_origins + 256, ny, nx, crop, H, W, clip, d_dst, s));
+  e->launches++;
+  if (!out_dev) {
+    CU(e, cudaMemcpyAsync(out, d_dst, nout, cudaMemcpyDeviceToHost, s));
+    CU(e, cudaStreamSynchronize(s));
+  }
+  return EMD_OK;
+}
+
+int emd_denoise_image(emd_engine* e, const void* img, int H, int W, int overlap, int flags, int mode, double* out,
+                      void* stream) {
+  if (!e || !img || !out) return EMD_EINVAL;
+  int rc = check_mode(e, mode);
+  if (rc) return rc;
+  const int crop = e->S;
+  if (H < crop || W < crop) return fail(e, EMD_EINVAL, "image %dx%d smaller than the %d crop", H, W, crop);
+  const bool f64 = flags & EMD_FLAG_INPUT_F64;
+  if (f64 && !(flags & EMD_FLAG_PREPROCESS)) return fail(e, EMD_EINVAL, "float64 input needs EMD_FLAG_PREPROCESS");
+  CU(e, cudaSetDevice(e->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  int ys[256], xs[256], ny = 0, nx = 0;
+  if (H / (crop - overlap) + 1 > 256 || W / (crop - overlap) + 1 > 256) return fail(e, EMD_EINVAL, "image too large");
+  if (emd_plan_tiles(H, W, crop, overlap, ys, xs, &ny, &nx)) return fail(e, EMD_EINVAL, "bad tiling arguments");
+  if ((rc = upload_origins(e, ys, xs, ny, nx, s))) return rc;
+  const size_t npx = (size_t)H * W, esz = f64 ? 8 : 4;
+  const int T = ny * nx;
+  const size_t ncr = (size_t)T * crop * crop * 4;
+  // image to device
+  const void* d_raw = img;
+  if (!is_device_ptr(img)) {
+    if ((rc = grow(e, reinterpret_cast<char**>(&e->d_img_raw), &e->img_raw_bytes, npx * esz))) return rc;
+    CU(e, cudaMemcpyAsync(e->d_img_raw, img, npx * esz, cudaMemcpyHostToDevice, s));
+    d_raw = e->d_img_raw;
+  }
+  const float* d_norm = reinterpret_cast<const float*>(d_raw);
+  if (flags & EMD_FLAG_PREPROCESS) {
+    if ((rc = grow(e, &e->d_img, &e->img_bytes, npx * 4))) return rc;
+    CU(e, launch_minmax(d_raw, f64, npx, e->d_minmax, e->d_partial, s));
+    CU(e, launch_normalise_apply(d_raw, f64, npx, e->d_minmax, e->d_img, s));
+    e->launches += 3;
+    d_norm = e->d_img;
+  }
+  if (e->crops_bytes < ncr) {
+    if (e->d_tiles) { cudaFree(e->d_tiles); e->d_tiles = nullptr; }
+    if ((rc = grow(e, &e->d_crops, &e->crops_bytes, ncr))) return rc;
+  }
+  if (!e->d_tiles) CU(e, cudaMalloc(&e->d_tiles, e->crops_bytes));
+  CU(e, launch_gather(d_norm, H, W, e->d_origins, e->d_origins + 256, ny, nx, crop, e->d_crops, s));
+  e->launches++;
+  const size_t per = (size_t)crop * crop;
+  for (int c0 = 0; c0 < T; c0 += e->max_batch) {
+    const int nb = std::min(e->max_batch, T - c0);
+    if ((rc = run_network(e, e->d_crops + c0 * per, e->d_tiles + c0 * per, nb, mode, s))) return rc;
+  }
+  double* d_dst = out;
+  const bool out_dev = is_device_ptr(out);
+  if (!out_dev) {
+    if ((rc = grow(e, &e->d_sout, &e->sout_bytes, npx * 8))) return rc;
+    d_dst = e->d_sout;
+  }
+  CU(e, launch_stitch(e->d_tiles, e->d_origins, e->d_origins + 256, ny, nx, crop, H, W,
+                      (flags & EMD_FLAG_POSTPROCESS) ? 1 : 0, d_dst, s));
+  e->launches++;
+  if (!out_dev) {
+    CU(e, cudaMemcpyAsync(out, d_dst, npx * 8, cudaMemcpyDeviceToHost, s));
+    CU(e, cudaStreamSynchronize(s));
+  }
+  return EMD_OK;
+}
+
+int emd_set_keep_activations(emd_engine* e, int keep) {
+  if (!e) return EMD_EINVAL;
+  CU(e, cudaSetDevice(e->device));
+  CU(e, cudaStreamSynchronize(e->stream));
+  e->keep = keep != 0;
+  return plan_arena(e);
+}
+
+// copy a (possibly channel-sliced) activation view of n images to host as dense f32 NHWC
+static int download_view(emd_engine* e, const View& v, int n, int et, bool is_f32, float* host_out, cudaStream_t s) {
+  const size_t px = (size_t)n * v.H * v.W, esz = is_f32 ? 4 : elem_size(et);
+  char* dense = nullptr; float* f32 = nullptr;
+  CU(e, cudaMalloc(&dense, px * v.C * esz));
+  CU(e, cudaMemcpy2DAsync(dense, v.C * esz, reinterpret_cast<const char*>(v.ptr) + (size_t)v.coff * esz, v.pitch * esz,
+                          v.C * esz, px, cudaMemcpyDeviceToDevice, s));
+  const void* src = dense;
+  if (!is_f32 && et != ET_F32) {
+    CU(e, cudaMalloc(&f32, px * v.C * 4));
+    CU(e, launch_uncast(dense, f32, px * v.C, et, s));
+    src = f32;
+  }
+  CU(e, cudaMemcpyAsync(host_out, src, px * v.C * 4, cudaMemcpyDeviceToHost, s));
+  CU(e, cudaStreamSynchronize(s));
+  cudaFree(dense);
+  if (f32) cudaFree(f32);
+  return EMD_OK;
+}
+
+int emd_get_activation(emd_engine* e, const char* name, float* out, size_t cap_elems, int dims[4]) {
+  if (!e || !name || !dims) return EMD_EINVAL;
+  auto it = e->named.find(name);
+  if (it == e->named.end()) return fail(e, EMD_EINVAL, "no activation named %s", name);
+  if (!e->keep) return fail(e, EMD_ESTATE, "emd_set_keep_activations(e,1) before the forward pass");
+  if (e->last_n <= 0) return fail(e, EMD_ESTATE, "no forward pass yet");
+  const Ref r = it->second;
+  const Tensor& t = e->tensors[r.t];
+  if (t.external) return fail(e, EMD_EINVAL, "%s is an I/O tensor", name);
+  dims[0] = e->last_n; dims[1] = t.H; dims[2] = t.W; dims[3] = r.C;
+  const size_t need = (size_t)e->last_n * t.H * t.W * r.C;
+  if (!out) return EMD_OK;  // size query
+  if (cap_elems < need) return fail(e, EMD_EINVAL, "buffer holds %zu elements, %zu needed", cap_elems, need);
+  CU(e, cudaSetDevice(e->device));
+  View v; v.ptr = e->arena + t.offset; v.H = t.H; v.W = t.W; v.pitch = t.C; v.coff = r.coff; v.C = r.C;
+  return download_view(e, v, e->last_n, e->last_et, false, out, e->stream);
+}
+
+int emd_run_layer(emd_engine* e, const char* name, const float* in, const float* in2, int n, float* out,
+                  size_t out_cap_elems, int mode, int out_dims[4]) {
+  if (!e || !name || !in || !out_dims) return EMD_EINVAL;
+  int rc = check_mode(e, mode);
+  if (rc) return rc;
+  if (n < 1 || n > e->max_batch) return fail(e, EMD_EINVAL, "n=%d outside [1,%d]", n, e->max_batch);
+  std::vector<int> idx;
+  for (int i = 0; i < (int)e->steps.size(); ++i)
+    if (e->steps[i].layer == name) idx.push_back(i);
+  if (idx.empty()) return fail(e, EMD_EINVAL, "no layer named %s", name);
+  const Ref rin = e->steps[idx.front()].in, rout = e->steps[idx.back()].out;
+  Ref rres;
+  for (int i : idx) if (e->steps[i].res.t >= 0) rres = e->steps[i].res;
+  if (rres.t >= 0 && !in2) return fail(e, EMD_EINVAL, "layer %s needs the residual operand in2", name);
+  const Tensor &ti = e->tensors[rin.t], &to = e->tensors[rout.t];
+  out_dims[0] = n; out_dims[1] = to.H; out_dims[2] = to.W; out_dims[3] = rout.C;
+  const size_t n_out = (size_t)n * to.H * to.W * rout.C;
+  if (!out) return EMD_OK;
+  if (out_cap_elems < n_out) return fail(e, EMD_EINVAL, "out holds %zu elements, %zu needed", out_cap_elems, n_out);
+  CU(e, cudaSetDevice(e->device));
+  cudaStream_t s = e->stream;
+  const int et = mode == EMD_MODE_FP32 ? ET_F32 : (mode == EMD_MODE_BF16 ? ET_BF16 : ET_F16);
+  const size_t n_in = (size_t)n * ti.H * ti.W * rin.C;
+  float *d_f32 = nullptr; void *d_in = nullptr, *d_res = nullptr, *d_out = nullptr;
+  const size_t n_stage = std::max(n_in, n_out);
+  CU(e, cudaMalloc(&d_f32, n_stage * 4));
+  CU(e, cudaMalloc(&d_in, n_in * 4));
+  CU(e, cudaMalloc(&d_out, n_out * 4));
+  CU(e, cudaMemcpyAsync(d_f32, in, n_in * 4, cudaMemcpyHostToDevice, s));
+  CU(e, launch_cast(d_f32, d_in, n_in, ti.external ? ET_F32 : et, s));
+  if (rres.t >= 0) {
+    CU(e, cudaMalloc(&d_res, n_out * 4));
+    CU(e, cudaStreamSynchronize(s));
+    CU(e, cudaMemcpyAsync(d_f32, in2, n_out * 4, cudaMemcpyHostToDevice, s));
+    CU(e, launch_cast(d_f32, d_res, n_out, et, s));
+  }
+  ExecCtx c{e, et, n, s, reinterpret_cast<const float*>(d_in), reinterpret_cast<float*>(d_out), {}};
+  c.ov.push_back(Override{rin.t, d_in});
+  c.ov.push_back(Override{rout.t, d_out});
+  if (rres.t >= 0) c.ov.push_back(Override{rres.t, d_res});
+  for (int i : idx) {
+    cudaError_t r = run_step(c, e->steps[i]);
+    if (r != cudaSuccess) return fail(e, EMD_ECUDA, "step %s: %s", e->steps[i].name.c_str(), cudaGetErrorString(r));
+  }
+  View v; v.ptr = d_out; v.H = to.H; v.W = to.W; v.pitch = rout.C; v.coff = 0; v.C = rout.C;
+  rc = download_view(e, v, n, et, to.external, out, s);
+  CU(e, cudaStreamSynchronize(s));
+  cudaError_t last = cudaGetLastError();
+  cudaFree(d_f32); cudaFree(d_in); cudaFree(d_out);
+  if (d_res) cudaFree(d_res);
+  if (last != cudaSuccess) return fail(e, EMD_ECUDA, "layer %s: %s", name, cudaGetErrorString(last));
+  return rc;
+}
+
+long long emd_kernel_launches(const emd_engine* e) { return e ? e->launches : -1; }
+
+int emd_set_profile(emd_engine* e, int on) {
+  if (!e) return EMD_EINVAL;
+  e->profile = on != 0;
+  return EMD_OK;
+}
+
+int emd_num_steps(const emd_engine* e) { return e ? (int)e->steps.size() : -1; }
+
+int emd_step_info(const emd_engine* e, int idx, char* name, size_t name_cap, float* ms, double* flops, double* bytes) {
+  if (!e || idx < 0 || idx >= (int)e->steps.size()) return EMD_EINVAL;
+  const Step& s = e->steps[idx];
+  if (name && name_cap) { strncpy(name, s.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (ms) *ms = s.ms;
+  if (flops) *flops = s.flops;
+  if (bytes) *bytes = s.bytes;
+  return EMD_OK;
+}
+
+}  // extern "C"

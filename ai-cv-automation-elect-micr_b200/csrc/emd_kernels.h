@@ -1,0 +1,89 @@
+// emd_kernels.h -- parameter blocks and launchers shared by the engine and the kernel files.
+// All activations are NHWC; "pitch" is the channel count of the *allocated* tensor (a layer may
+// read/write a channel slice [coff, coff+C) of a wider tensor -- that is how concats are formed
+// without a copy, DMG:348-350 / 497-499 / 509-511).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace emd {
+
+enum ElemType { ET_F32 = 0, ET_BF16 = 1, ET_F16 = 2 };
+static inline size_t elem_size(int et) { return et == ET_F32 ? 4 : 2; }
+
+// View of an NHWC activation (possibly a channel slice of a wider tensor).
+struct View {
+  void* ptr;      // base of the allocated tensor for image 0
+  int H, W;       // spatial size per image
+  int pitch;      // channels of the allocated tensor
+  int coff;       // first channel of this view
+  int C;          // channels of this view
+};
+
+// Implicit-GEMM convolution:  D[m, co] = sum_t sum_ci  X[pix(m, t), ci] * Wt[(wrow[t]*Cin + ci), co]
+// over a virtual output grid m = (n, my, mx) in N x MH x MW;
+//   input pixel  (my*istride + dy[t], mx*istride + dx[t])  (out of range -> 0, TF SAME padding)
+//   output pixel (my*ostride + oy0,   mx*ostride + ox0)    (ostride 2 = one phase of a transposed conv)
+// epilogue: v = acc*scale[co] + shift[co]; relu6?; clip01?; v += residual?; store.
+struct ConvParams {
+  View in, out, res;         // res.ptr == nullptr: no residual
+  int N, MH, MW;
+  int istride, ostride, oy0, ox0;
+  int ntaps;
+  int dy[9], dx[9], wrow[9];
+  int Cin, Cout;
+  const float* w;            // FP32 [ktaps*Cin][Cout] (TF kernel layout flattened)
+  const void* w16;           // 16-bit operand copy, UMMA tile-swizzled (emd_umma.cu); may be null
+  const float* scale;        // [Cout]
+  const float* shift;        // [Cout]
+  int relu6, clip01;
+  int out_f32;               // output tensor is float regardless of the element type (final layer)
+  int in_f32;                // input tensor is float regardless of the element type (network input)
+};
+
+struct DwParams {
+  View in, out;
+  int N, OH, OW;
+  int stride, rate, pad;     // input row = oy*stride - pad + ky*rate
+  const float* w;            // [9][C] FP32, tap-major
+  int in_f32;
+};
+
+struct ResizeParams {        // TF1 legacy bilinear (DMG:344, 494) + optional affine/ReLU6 (DMG:345)
+  View in, out;
+  int N;
+  const float* scale;        // may be null
+  const float* shift;
+  int relu6;
+};
+
+struct PoolParams { View in, out; int N; };   // 2x2 average, stride 2 (DMG:331-335)
+
+// launchers (emd_kernels_simt.cu); et = element type of the activations
+cudaError_t launch_conv_simt(const ConvParams& p, int et, cudaStream_t s);
+cudaError_t launch_dw3x3(const DwParams& p, int et, cudaStream_t s);
+cudaError_t launch_resize(const ResizeParams& p, int et, cudaStream_t s);
+cudaError_t launch_avgpool(const PoolParams& p, int et, cudaStream_t s);
+cudaError_t launch_cast(const float* src, void* dst, size_t n, int et, cudaStream_t s);
+cudaError_t launch_uncast(const void* src, float* dst, size_t n, int et, cudaStream_t s);
+
+// emd_umma.cu: tcgen05 implicit GEMM (16-bit element types only)
+bool umma_supported(const ConvParams& p, int et);
+cudaError_t launch_conv_umma(const ConvParams& p, int et, int num_sms, cudaStream_t s);
+// packs FP32 [K][Cout] weights into the UMMA tile image; returns bytes needed when dst == nullptr
+size_t umma_pack_weights(const float* w, int ntaps, int Cin, int Cout, int et, void* dst_host);
+
+// emd_kernels_wrap.cu: whole-image wrapper kernels
+cudaError_t launch_minmax(const void* img, int in_f64, size_t n, double* d_minmax /*[2]*/, void* d_partial,
+                          cudaStream_t s);
+cudaError_t launch_normalise_apply(const void* img, int in_f64, size_t n, const double* d_minmax, float* out,
+                                   cudaStream_t s);
+cudaError_t launch_gather(const float* img, int H, int W, const int* d_ys, const int* d_xs, int ny, int nx,
+                          int crop, float* crops, cudaStream_t s);
+cudaError_t launch_stitch(const float* tiles, const int* d_ys, const int* d_xs, int ny, int nx, int crop, int H,
+                          int W, int clip, double* out, cudaStream_t s);
+size_t minmax_partial_bytes();
+
+}  // namespace emd

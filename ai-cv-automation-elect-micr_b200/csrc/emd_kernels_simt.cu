@@ -1,0 +1,438 @@
+// emd_kernels_simt.cu -- CUDA-core kernels.
+//
+//  * conv_simt_kernel: FP32-accumulate implicit-GEMM convolution on CUDA cores.  It is the FP32
+//    validation mode of every GEMM-class layer (strided_conv_block pointwise DMG:250-276,
+//    residual_conv DMG:363-373, ASPP DMG:291-361, conv_block_not_sep DMG:225-238, deconv_block
+//    DMG:278-289 as 4 sub-pixel phases) and the fallback of the 16-bit modes for shapes the
+//    tcgen05 kernel does not take.
+//  * dw3x3_kernel: depthwise 3x3 (stride / rate in the depthwise stage, App. A.2), memory-bound.
+//  * resize / avgpool / cast: memory-bound helpers (DMG:331-345, 494).
+#include "emd_kernels.h"
+
+namespace emd {
+
+// ---------------------------------------------------------------------------------------------
+// element helpers
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct ElemOf;
+template <> struct ElemOf<float> { static constexpr int et = ET_F32; };
+template <> struct ElemOf<__nv_bfloat16> { static constexpr int et = ET_BF16; };
+template <> struct ElemOf<__half> { static constexpr int et = ET_F16; };
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+template <typename T, int V> struct VecIO;
+template <> struct VecIO<float, 4> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct VecIO<float, 8> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) {
+    VecIO<float, 4>::ld(p, v); VecIO<float, 4>::ld(p + 4, v + 4);
+  }
+  static __device__ __forceinline__ void st(float* p, const float* v) {
+    VecIO<float, 4>::st(p, v); VecIO<float, 4>::st(p + 4, v + 4);
+  }
+};
+template <typename T> struct Pair;
+template <> struct Pair<__nv_bfloat16> {
+  using type = __nv_bfloat162;
+  static __device__ __forceinline__ float2 up(type v) { return __bfloat1622float2(v); }
+  static __device__ __forceinline__ type down(float a, float b) { return __floats2bfloat162_rn(a, b); }
+};
+template <> struct Pair<__half> {
+  using type = __half2;
+  static __device__ __forceinline__ float2 up(type v) { return __half22float2(v); }
+  static __device__ __forceinline__ type down(float a, float b) { return __floats2half2_rn(a, b); }
+};
+template <typename T> struct VecIO<T, 4> {  // 16-bit types, 8 bytes
+  using P = Pair<T>;
+  static __device__ __forceinline__ void ld(const T* p, float* v) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    float2 a = P::up(*reinterpret_cast<typename P::type*>(&u.x));
+    float2 b = P::up(*reinterpret_cast<typename P::type*>(&u.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void st(T* p, const float* v) {
+    uint2 u;
+    typename P::type a = P::down(v[0], v[1]), b = P::down(v[2], v[3]);
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+template <typename T> struct VecIO<T, 8> {  // 16-bit types, 16 bytes
+  using P = Pair<T>;
+  static __device__ __forceinline__ void ld(const T* p, float* v) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t t = w[i];
+      float2 a = P::up(*reinterpret_cast<typename P::type*>(&t));
+      v[2 * i] = a.x; v[2 * i + 1] = a.y;
+    }
+  }
+  static __device__ __forceinline__ void st(T* p, const float* v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      typename P::type a = P::down(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&a);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <typename T> struct VecIO<T, 1> {
+  static __device__ __forceinline__ void ld(const T* p, float* v) { v[0] = to_f(*p); }
+  static __device__ __forceinline__ void st(T* p, const float* v) { *p = from_f<T>(v[0]); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// implicit-GEMM convolution, CUDA cores, FP32 accumulate.  64x64x16 tiles, 4x4 per thread.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const long long M = (long long)p.N * p.MH * p.MW;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  // A-load role: row lr, channels kq*4..kq*4+3 of the K chunk
+  const int lr = tid >> 2, kq = tid & 3;
+  const long long mrow = m0 + lr;
+  const bool mvalid = mrow < M;
+  int n_img = 0, my = 0, mx = 0;
+  if (mvalid) {
+    n_img = (int)(mrow / ((long long)p.MH * p.MW));
+    int rem = (int)(mrow - (long long)n_img * p.MH * p.MW);
+    my = rem / p.MW; mx = rem - my * p.MW;
+  }
+  const bool a_vec = ((p.in.pitch | p.in.coff | p.Cin) & 3) == 0;
+  // B-load role: k row bk, columns bn..bn+3
+  const int bk = tid >> 4, bn = (tid & 15) * 4;
+  const bool b_vec = (p.Cout & 3) == 0;
+  // compute role
+  const int ty = tid >> 4, tx = tid & 15;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int t = 0; t < p.ntaps; ++t) {
+    const int iy = my * p.istride + p.dy[t], ix = mx * p.istride + p.dx[t];
+    const bool valid = mvalid && iy >= 0 && iy < p.in.H && ix >= 0 && ix < p.in.W;
+    const size_t src_off = valid ? (((size_t)n_img * p.in.H + iy) * p.in.W + ix) * p.in.pitch + p.in.coff : 0;
+    const size_t wbase = (size_t)p.wrow[t] * p.Cin;
+    for (int c0 = 0; c0 < p.Cin; c0 += BK) {
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      const int c = c0 + kq * 4;
+      if (valid && c < p.Cin) {
+        if (p.in_f32) {
+          const float* src = reinterpret_cast<const float*>(p.in.ptr) + src_off + c;
+          if (a_vec) VecIO<float, 4>::ld(src, a);
+          else
+            for (int j = 0; j < 4; ++j) if (c + j < p.Cin) a[j] = src[j];
+        } else {
+          const T* src = reinterpret_cast<const T*>(p.in.ptr) + src_off + c;
+          if (a_vec) VecIO<T, 4>::ld(src, a);
+          else
+            for (int j = 0; j < 4; ++j) if (c + j < p.Cin) a[j] = to_f(src[j]);
+        }
+      }
+      float b[4] = {0.f, 0.f, 0.f, 0.f};
+      if (c0 + bk < p.Cin) {
+        const float* wp = p.w + (wbase + c0 + bk) * p.Cout + n0 + bn;
+        if (b_vec && n0 + bn + 3 < p.Cout) VecIO<float, 4>::ld(wp, b);
+        else
+          for (int j = 0; j < 4; ++j) if (n0 + bn + j < p.Cout) b[j] = wp[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) As[kq * 4 + j][lr] = a[j];
+      *reinterpret_cast<float4*>(&Bs[bk][bn]) = make_float4(b[0], b[1], b[2], b[3]);
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float aa[4] = {av.x, av.y, av.z, av.w};
+        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  // epilogue: folded BN (+bias) -> ReLU6 -> clip -> + residual -> store
+  const int cbase = n0 + tx * 4;
+  if (cbase >= p.Cout) return;
+  float sc[4], sh[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = min(cbase + j, p.Cout - 1);
+    sc[j] = p.scale[c]; sh[j] = p.shift[c];
+  }
+  const bool o_vec = ((p.out.pitch | p.out.coff | p.Cout) & 3) == 0;
+  const bool r_vec = p.res.ptr && ((p.res.pitch | p.res.coff) & 3) == 0 && o_vec;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int ni = (int)(m / ((long long)p.MH * p.MW));
+    const int rem = (int)(m - (long long)ni * p.MH * p.MW);
+    const int oy = (rem / p.MW) * p.ostride + p.oy0, ox = (rem % p.MW) * p.ostride + p.ox0;
+    const size_t pix = ((size_t)ni * p.out.H + oy) * p.out.W + ox;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x = fmaf(acc[i][j], sc[j], sh[j]);
+      if (p.relu6) x = fminf(fmaxf(x, 0.f), 6.f);
+      if (p.clip01) x = fminf(fmaxf(x, 0.f), 1.f);
+      v[j] = x;
+    }
+    if (p.res.ptr) {
+      const T* rp = reinterpret_cast<const T*>(p.res.ptr) + pix * p.res.pitch + p.res.coff + cbase;
+      float r[4] = {0.f, 0.f, 0.f, 0.f};
+      if (r_vec) VecIO<T, 4>::ld(rp, r);
+      else
+        for (int j = 0; j < 4; ++j) if (cbase + j < p.Cout) r[j] = to_f(rp[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] += r[j];
+    }
+    if (p.out_f32) {
+      float* op = reinterpret_cast<float*>(p.out.ptr) + pix * p.out.pitch + p.out.coff + cbase;
+      if (o_vec) VecIO<float, 4>::st(op, v);
+      else
+        for (int j = 0; j < 4; ++j) if (cbase + j < p.Cout) op[j] = v[j];
+    } else {
+      T* op = reinterpret_cast<T*>(p.out.ptr) + pix * p.out.pitch + p.out.coff + cbase;
+      if (o_vec) VecIO<T, 4>::st(op, v);
+      else
+        for (int j = 0; j < 4; ++j) if (cbase + j < p.Cout) op[j] = from_f<T>(v[j]);
+    }
+  }
+}
+
+cudaError_t launch_conv_simt(const ConvParams& p, int et, cudaStream_t s) {
+  const long long M = (long long)p.N * p.MH * p.MW;
+  dim3 grid((unsigned)((M + 63) / 64), (unsigned)((p.Cout + 63) / 64));
+  if (et == ET_F32) conv_simt_kernel<float><<<grid, 256, 0, s>>>(p);
+  else if (et == ET_BF16) conv_simt_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p);
+  else conv_simt_kernel<__half><<<grid, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// depthwise 3x3 (DepthwiseConv2dNative of slim.separable_convolution2d, DMG:253-273)
+// ---------------------------------------------------------------------------------------------
+template <typename TI, typename TO, int V>
+__global__ void __launch_bounds__(256) dw3x3_kernel(const DwParams p) {
+  const int C = p.in.C;
+  const int cg = C / V;
+  const long long total = (long long)p.N * p.OH * p.OW * cg;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % cg);
+  long long pix = idx / cg;
+  const int ox = (int)(pix % p.OW); pix /= p.OW;
+  const int oy = (int)(pix % p.OH);
+  const int n = (int)(pix / p.OH);
+  float acc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = 0.f;
+  const TI* base = reinterpret_cast<const TI*>(p.in.ptr);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * p.stride - p.pad + ky * p.rate;
+    if (iy < 0 || iy >= p.in.H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * p.stride - p.pad + kx * p.rate;
+      if (ix < 0 || ix >= p.in.W) continue;
+      float x[V], w[V];
+      VecIO<TI, V>::ld(base + (((size_t)n * p.in.H + iy) * p.in.W + ix) * p.in.pitch + p.in.coff + g * V, x);
+      VecIO<float, V>::ld(p.w + (ky * 3 + kx) * C + g * V, w);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = fmaf(x[j], w[j], acc[j]);
+    }
+  }
+  TO* op = reinterpret_cast<TO*>(p.out.ptr) +
+           (((size_t)n * p.out.H + oy) * p.out.W + ox) * p.out.pitch + p.out.coff + g * V;
+  VecIO<TO, V>::st(op, acc);
+}
+
+template <typename TI, typename TO>
+static cudaError_t launch_dw_t(const DwParams& p, cudaStream_t s) {
+  const int C = p.in.C;
+  const bool al8 = ((C | p.in.pitch | p.in.coff | p.out.pitch | p.out.coff) & 7) == 0;
+  const bool al4 = ((C | p.in.pitch | p.in.coff | p.out.pitch | p.out.coff) & 3) == 0;
+  const long long px = (long long)p.N * p.OH * p.OW;
+  if (sizeof(TI) == 2 && sizeof(TO) == 2 && al8) {
+    long long total = px * (C / 8);
+    dw3x3_kernel<TI, TO, 8><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
+  } else if (al4) {
+    long long total = px * (C / 4);
+    dw3x3_kernel<TI, TO, 4><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
+  } else {
+    long long total = px * C;
+    dw3x3_kernel<TI, TO, 1><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dw3x3(const DwParams& p, int et, cudaStream_t s) {
+  if (et == ET_F32) return launch_dw_t<float, float>(p, s);
+  if (et == ET_BF16)
+    return p.in_f32 ? launch_dw_t<float, __nv_bfloat16>(p, s) : launch_dw_t<__nv_bfloat16, __nv_bfloat16>(p, s);
+  return p.in_f32 ? launch_dw_t<float, __half>(p, s) : launch_dw_t<__half, __half>(p, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TF1 legacy bilinear resize (align_corners=False, no half-pixel centres; DMG:344, 494) with an
+// optional per-channel affine + ReLU6 (the BN/ReLU6 that follows the image-level branch, DMG:345)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(256) resize_kernel(const ResizeParams p) {
+  const int C = p.in.C, cg = C / V;
+  const long long total = (long long)p.N * p.out.H * p.out.W * cg;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % cg);
+  long long pix = idx / cg;
+  const int ox = (int)(pix % p.out.W); pix /= p.out.W;
+  const int oy = (int)(pix % p.out.H);
+  const int n = (int)(pix / p.out.H);
+  const float sy = oy * ((float)p.in.H / (float)p.out.H), sx = ox * ((float)p.in.W / (float)p.out.W);
+  const int y0 = (int)floorf(sy), x0 = (int)floorf(sx);
+  const int y1 = min(y0 + 1, p.in.H - 1), x1 = min(x0 + 1, p.in.W - 1);
+  const float wy = sy - y0, wx = sx - x0;
+  const T* base = reinterpret_cast<const T*>(p.in.ptr) + (size_t)n * p.in.H * p.in.W * p.in.pitch + p.in.coff + g * V;
+  float tl[V], tr[V], bl[V], br[V], o[V];
+  VecIO<T, V>::ld(base + ((size_t)y0 * p.in.W + x0) * p.in.pitch, tl);
+  VecIO<T, V>::ld(base + ((size_t)y0 * p.in.W + x1) * p.in.pitch, tr);
+  VecIO<T, V>::ld(base + ((size_t)y1 * p.in.W + x0) * p.in.pitch, bl);
+  VecIO<T, V>::ld(base + ((size_t)y1 * p.in.W + x1) * p.in.pitch, br);
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const float top = tl[j] + (tr[j] - tl[j]) * wx;
+    const float bot = bl[j] + (br[j] - bl[j]) * wx;
+    float v = top + (bot - top) * wy;
+    if (p.scale) v = fmaf(v, p.scale[g * V + j], p.shift[g * V + j]);
+    if (p.relu6) v = fminf(fmaxf(v, 0.f), 6.f);
+    o[j] = v;
+  }
+  T* op = reinterpret_cast<T*>(p.out.ptr) + (((size_t)n * p.out.H + oy) * p.out.W + ox) * p.out.pitch + p.out.coff + g * V;
+  VecIO<T, V>::st(op, o);
+}
+
+template <typename T>
+static cudaError_t launch_resize_t(const ResizeParams& p, cudaStream_t s) {
+  const int C = p.in.C;
+  const bool al8 = ((C | p.in.pitch | p.in.coff | p.out.pitch | p.out.coff) & 7) == 0;
+  const long long px = (long long)p.N * p.out.H * p.out.W;
+  if (sizeof(T) == 2 && al8) {
+    long long total = px * (C / 8);
+    resize_kernel<T, 8><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
+  } else {
+    long long total = px * (C / 4);
+    resize_kernel<T, 4><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
+  }
+  return cudaGetLastError();
+}
+cudaError_t launch_resize(const ResizeParams& p, int et, cudaStream_t s) {
+  if (et == ET_F32) return launch_resize_t<float>(p, s);
+  if (et == ET_BF16) return launch_resize_t<__nv_bfloat16>(p, s);
+  return launch_resize_t<__half>(p, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2x2 average pool, stride 2 (tf.nn.pool AVG SAME on even sizes, DMG:331-335)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(256) avgpool_kernel(const PoolParams p) {
+  const int C = p.in.C, cg = C / V;
+  const long long total = (long long)p.N * p.out.H * p.out.W * cg;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % cg);
+  long long pix = idx / cg;
+  const int ox = (int)(pix % p.out.W); pix /= p.out.W;
+  const int oy = (int)(pix % p.out.H);
+  const int n = (int)(pix / p.out.H);
+  const T* base = reinterpret_cast<const T*>(p.in.ptr) + (size_t)n * p.in.H * p.in.W * p.in.pitch + p.in.coff + g * V;
+  float a[V], b[V], c[V], d[V], o[V];
+  VecIO<T, V>::ld(base + ((size_t)(2 * oy) * p.in.W + 2 * ox) * p.in.pitch, a);
+  VecIO<T, V>::ld(base + ((size_t)(2 * oy) * p.in.W + 2 * ox + 1) * p.in.pitch, b);
+  VecIO<T, V>::ld(base + ((size_t)(2 * oy + 1) * p.in.W + 2 * ox) * p.in.pitch, c);
+  VecIO<T, V>::ld(base + ((size_t)(2 * oy + 1) * p.in.W + 2 * ox + 1) * p.in.pitch, d);
+#pragma unroll
+  for (int j = 0; j < V; ++j) o[j] = ((a[j] + b[j]) + (c[j] + d[j])) * 0.25f;
+  T* op = reinterpret_cast<T*>(p.out.ptr) + (((size_t)n * p.out.H + oy) * p.out.W + ox) * p.out.pitch + p.out.coff + g * V;
+  VecIO<T, V>::st(op, o);
+}
+template <typename T>
+static cudaError_t launch_avgpool_t(const PoolParams& p, cudaStream_t s) {
+  const int C = p.in.C;
+  const bool al8 = ((C | p.in.pitch | p.in.coff | p.out.pitch | p.out.coff) & 7) == 0;
+  const long long px = (long long)p.N * p.out.H * p.out.W;
+  if (sizeof(T) == 2 && al8) {
+    long long total = px * (C / 8);
+    avgpool_kernel<T, 8><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
+  } else {
+    long long total = px * (C / 4);
+    avgpool_kernel<T, 4><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
+  }
+  return cudaGetLastError();
+}
+cudaError_t launch_avgpool(const PoolParams& p, int et, cudaStream_t s) {
+  if (et == ET_F32) return launch_avgpool_t<float>(p, s);
+  if (et == ET_BF16) return launch_avgpool_t<__nv_bfloat16>(p, s);
+  return launch_avgpool_t<__half>(p, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// casts between the f32 I/O tensors and the activation element type
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void cast_kernel(const float* __restrict__ src, T* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = from_f<T>(src[i]);
+}
+template <typename T>
+__global__ void uncast_kernel(const T* __restrict__ src, float* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = to_f(src[i]);
+}
+static unsigned grid_for(size_t n) { return (unsigned)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256); }
+cudaError_t launch_cast(const float* src, void* dst, size_t n, int et, cudaStream_t s) {
+  if (et == ET_F32) return cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, s);
+  if (et == ET_BF16) cast_kernel<<<grid_for(n), 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  else cast_kernel<<<grid_for(n), 256, 0, s>>>(src, reinterpret_cast<__half*>(dst), n);
+  return cudaGetLastError();
+}
+cudaError_t launch_uncast(const void* src, float* dst, size_t n, int et, cudaStream_t s) {
+  if (et == ET_F32) return cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, s);
+  if (et == ET_BF16) uncast_kernel<<<grid_for(n), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
+  else uncast_kernel<<<grid_for(n), 256, 0, s>>>(reinterpret_cast<const __half*>(src), dst, n);
+  return cudaGetLastError();
+}
+
+}  // namespace emd

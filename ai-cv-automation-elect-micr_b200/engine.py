@@ -1,0 +1,173 @@
+"""Thin Python handle over the C ABI (include/emd.h).  Tensor plumbing only: numpy arrays or
+torch tensors go in as raw pointers; all arithmetic happens in libemd.so on the GPU."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import MODES
+
+
+def _ptr(x):
+    """Raw address of a numpy array or a torch tensor (host or CUDA)."""
+    if isinstance(x, np.ndarray):
+        return C.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    raise TypeError(f"unsupported buffer type {type(x)}")
+
+
+class Engine:
+    """One GPU + weights + workspace (an ``emd_engine``).  Not thread-safe (emd.h)."""
+
+    def __init__(self, device: int = 0, cropsize: int = 512, max_batch: int = 8, variant: str = "A"):
+        self.lib = _lib.load()
+        self.S = cropsize
+        self.device = device
+        self.max_batch = max_batch
+        h = C.c_void_p()
+        rc = self.lib.emd_create(C.byref(h), device, cropsize, 0 if variant == "A" else 1, max_batch)
+        if rc != 0:
+            raise RuntimeError(f"emd_create failed ({rc}): {self.lib.emd_last_error(None).decode()}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.emd_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.emd_last_error(self.h).decode()}")
+
+    def load_weights(self, blob: bytes):
+        self._blob = blob
+        self._check(self.lib.emd_load_weights(self.h, C.c_char_p(blob), len(blob)), "emd_load_weights")
+
+    # -- network ---------------------------------------------------------------------------
+    def forward(self, crops, out=None, mode="bf16", stream=None):
+        """crops [n,S,S] float32 (numpy, or torch host/CUDA tensor) -> [n,S,S] float32."""
+        n = int(crops.shape[0])
+        if tuple(crops.shape[1:3]) != (self.S, self.S):
+            raise ValueError(f"crops must be [n,{self.S},{self.S}], got {tuple(crops.shape)}")
+        if out is None:
+            if isinstance(crops, np.ndarray):
+                out = np.empty((n, self.S, self.S), np.float32)
+            else:
+                import torch
+                out = torch.empty((n, self.S, self.S), dtype=torch.float32, device=crops.device)
+        self._check(self.lib.emd_forward(self.h, _ptr(crops), n, _ptr(out), MODES[mode],
+                                         C.c_void_p(stream) if stream else None), "emd_forward")
+        return out
+
+    def run_layer(self, name, x, res=None, mode="fp32"):
+        """One fused layer on NHWC float32 host inputs (parity hook)."""
+        x = np.ascontiguousarray(x, np.float32)
+        n = x.shape[0]
+        dims = (C.c_int * 4)()
+        r = None if res is None else np.ascontiguousarray(res, np.float32)
+        self._check(self.lib.emd_run_layer(self.h, name.encode(), _ptr(x), None if r is None else _ptr(r), n,
+                                           None, 0, MODES[mode], dims), "emd_run_layer(size)")
+        out = np.empty(tuple(dims), np.float32)
+        self._check(self.lib.emd_run_layer(self.h, name.encode(), _ptr(x), None if r is None else _ptr(r), n,
+                                           _ptr(out), out.size, MODES[mode], dims), f"emd_run_layer({name})")
+        return out
+
+    def set_keep_activations(self, keep=True):
+        self._check(self.lib.emd_set_keep_activations(self.h, int(keep)), "emd_set_keep_activations")
+
+    def activation(self, name):
+        dims = (C.c_int * 4)()
+        self._check(self.lib.emd_get_activation(self.h, name.encode(), None, 0, dims), "emd_get_activation(size)")
+        out = np.empty(tuple(dims), np.float32)
+        self._check(self.lib.emd_get_activation(self.h, name.encode(), _ptr(out), out.size, dims),
+                    f"emd_get_activation({name})")
+        return out
+
+    # -- wrapper pieces ----------------------------------------------------------------------
+    def plan_tiles(self, H, W, crop=None, overlap=80):
+        crop = crop or self.S
+        if crop <= 0 or not 0 <= overlap < crop or H < crop or W < crop:
+            raise ValueError(f"cannot tile a {H}x{W} image with crop {crop}, overlap {overlap}")
+        cap = max(H, W) // (crop - overlap) + 2
+        ys, xs = (C.c_int * cap)(), (C.c_int * cap)()
+        ny, nx = C.c_int(), C.c_int()
+        rc = self.lib.emd_plan_tiles(H, W, crop, overlap, ys, xs, C.byref(ny), C.byref(nx))
+        if rc != 0:
+            raise ValueError(f"emd_plan_tiles({H},{W},{crop},{overlap}) failed ({rc})")
+        return list(ys[: ny.value]), list(xs[: nx.value])
+
+    def normalise(self, img):
+        img = np.ascontiguousarray(img)
+        if img.dtype not in (np.float32, np.float64):
+            img = img.astype(np.float32)
+        out = np.empty(img.shape, np.float32)
+        self._check(self.lib.emd_normalise(self.h, _ptr(img), int(img.dtype == np.float64), img.shape[0],
+                                           img.shape[1], _ptr(out), None), "emd_normalise")
+        return out
+
+    def gather_crops(self, img, ys, xs, crop=None):
+        crop = crop or self.S
+        img = np.ascontiguousarray(img, np.float32)
+        out = np.empty((len(ys) * len(xs), crop, crop), np.float32)
+        ya, xa = (C.c_int * len(ys))(*ys), (C.c_int * len(xs))(*xs)
+        self._check(self.lib.emd_gather_crops(self.h, _ptr(img), img.shape[0], img.shape[1], ya, xa, len(ys),
+                                              len(xs), crop, _ptr(out), None), "emd_gather_crops")
+        return out
+
+    def stitch(self, tiles, ys, xs, H, W, crop=None, clip=True):
+        crop = crop or self.S
+        tiles = np.ascontiguousarray(tiles, np.float32)
+        out = np.empty((H, W), np.float64)
+        ya, xa = (C.c_int * len(ys))(*ys), (C.c_int * len(xs))(*xs)
+        self._check(self.lib.emd_stitch(self.h, _ptr(tiles), ya, xa, len(ys), len(xs), crop, H, W, int(clip),
+                                        _ptr(out), None), "emd_stitch")
+        return out
+
+    def denoise_image(self, img, overlap=80, preprocess=True, postprocess=True, mode="bf16", out=None):
+        """Whole micrograph in one call: normalise -> tile -> batched forward -> stitch (emd_denoise_image)."""
+        is_np = isinstance(img, np.ndarray)
+        if is_np:
+            if img.dtype not in (np.float32, np.float64):
+                img = img.astype(np.float32)
+            if img.dtype == np.float64 and not preprocess:
+                img = img.astype(np.float32)
+            img = np.ascontiguousarray(img)
+            f64 = img.dtype == np.float64
+        else:
+            import torch
+            f64 = img.dtype == torch.float64
+        H, W = int(img.shape[0]), int(img.shape[1])
+        if out is None:
+            if is_np:
+                out = np.empty((H, W), np.float64)
+            else:
+                import torch
+                out = torch.empty((H, W), dtype=torch.float64, device=img.device)
+        flags = (_lib.EMD_FLAG_PREPROCESS if preprocess else 0) | (_lib.EMD_FLAG_POSTPROCESS if postprocess else 0) \
+            | (_lib.EMD_FLAG_INPUT_F64 if f64 else 0)
+        self._check(self.lib.emd_denoise_image(self.h, _ptr(img), H, W, overlap, flags, MODES[mode], _ptr(out),
+                                               None), "emd_denoise_image")
+        return out
+
+    # -- measurement ---------------------------------------------------------------------------
+    @property
+    def kernel_launches(self):
+        return int(self.lib.emd_kernel_launches(self.h))
+
+    def set_profile(self, on=True):
+        self._check(self.lib.emd_set_profile(self.h, int(on)), "emd_set_profile")
+
+    def step_info(self):
+        """[(name, ms, flops_per_crop, bytes_per_crop)] of the last profiled forward."""
+        out = []
+        name = C.create_string_buffer(64)
+        ms, fl, by = C.c_float(), C.c_double(), C.c_double()
+        for i in range(self.lib.emd_num_steps(self.h)):
+            self.lib.emd_step_info(self.h, i, name, 64, C.byref(ms), C.byref(fl), C.byref(by))
+            out.append((name.value.decode(), ms.value, fl.value, by.value))
+        return out

@@ -1,0 +1,126 @@
+/*
+ * emd.h -- C ABI of the B200-native electron-micrograph denoiser (libemd.so).
+ *
+ * This is the drop-in boundary for ONE path of Jeffrey-Ede/AI-CV-Automation-Elect-Micr:
+ * inference through the atrous-convolutional Xception encoder-decoder denoiser and its
+ * crop-tile / normalise / stitch wrapper.  Every entry point names the reference interface it
+ * replaces (paths relative to the reference tree):
+ *
+ *   DEN = machine_learning/denoiser.py          (the Denoiser class, variant-B graph)
+ *   DMG = misc_py/denoiser-multi-gpu.py         (canonical variant-A graph, normalise helpers)
+ *   TMP = misc_py/denoiser_class_function-tmp.py (stand-alone copy of Denoiser.denoise)
+ *
+ * Conventions
+ *   - plain C: opaque handle, plain pointers and sizes, no C++/torch types, no exceptions.
+ *   - every function returns 0 on success, a negative EMD_E* code on failure;
+ *     emd_last_error() gives the message.  A build without a usable CUDA device fails loudly
+ *     (EMD_ECUDA) -- there is no CPU fallback.
+ *   - image/crop pointers may be device pointers, pinned host pointers or pageable host pointers;
+ *     the library classifies them with cudaPointerGetAttributes.  With a host output pointer the
+ *     call returns after the result has landed; with device pointers it is asynchronous on
+ *     `stream` (a cudaStream_t passed as void*; NULL = the engine's own stream).
+ *   - a handle owns one device, its weights and its workspace; it is NOT thread-safe.  Handles on
+ *     different GPUs are independent (micrographs/crops shard image-wise, no collective).
+ */
+#ifndef EMD_H_
+#define EMD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMD_OK        0
+#define EMD_EINVAL   -1   /* bad argument / shape */
+#define EMD_ECUDA    -2   /* CUDA runtime error (message has the cudaError string) */
+#define EMD_ESTATE   -3   /* call order (e.g. forward before load_weights) */
+#define EMD_ENOMEM   -4
+
+/* arithmetic modes of the network */
+#define EMD_MODE_FP32 0   /* CUDA-core FP32 validation mode (parity gate 1e-5) */
+#define EMD_MODE_BF16 1   /* tcgen05/TMEM tensor-core path, BF16 operands, FP32 accumulate */
+#define EMD_MODE_FP16 2   /* same kernels with FP16 operands (all activations are ReLU6-bounded) */
+
+/* graph variants */
+#define EMD_VARIANT_A 0   /* DMG:200-540, dense dilated ASPP, in-graph clip */
+#define EMD_VARIANT_B 1   /* DEN:58-398 (not built yet: emd_create returns EMD_EINVAL) */
+
+/* emd_denoise_image flags */
+#define EMD_FLAG_PREPROCESS   1   /* DEN:655-656 (repaired): NaN/Inf->0.5 then scale0to1 */
+#define EMD_FLAG_POSTPROCESS  2   /* DEN:679-680: clip(0,1) */
+#define EMD_FLAG_INPUT_F64    4   /* img is const double* (np.random.rand in DEN:708 is float64) */
+
+typedef struct emd_engine emd_engine;
+
+int         emd_version(void);
+/* last error message of this handle (or, with NULL, of the last failed emd_create on this thread) */
+const char* emd_last_error(const emd_engine* e);
+
+/* Replaces Denoiser.__init__ (DEN:587-630): pins one GPU (DEN:591 CUDA_VISIBLE_DEVICES), builds the
+ * static layer schedule that stands in for get_model_fn/_tower_fn/architecture graph construction
+ * (DEN:463-581, DMG:200-540) for crops of `cropsize` (multiple of 16; reference: 512, DMG:112), and
+ * sizes the workspace for `max_batch` crops per pass (larger batches are processed in chunks). */
+int emd_create(emd_engine** out, int device, int cropsize, int variant, int max_batch);
+int emd_destroy(emd_engine* e);
+
+/* Replaces tf.train.Saver().restore (DEN:626-627): takes the packed weight blob produced by the
+ * host-side exporter (BN folded per DMG:210-223; layouts in DESIGN.md) and uploads FP32, BF16 and
+ * FP16 copies. */
+int emd_load_weights(emd_engine* e, const void* blob, size_t nbytes);
+
+/* Replaces sess.run(self._tower_preds, feed_dict=...) (DEN:646-647) = architecture() forward
+ * (DMG:392-540) for a batch: crops [n,S,S] f32 in -> out [n,S,S] f32 (variant A: clipped to [0,1]
+ * in-graph, DMG:534-538). */
+int emd_forward(emd_engine* e, const float* crops, int n, float* out, int mode, void* stream);
+
+/* Tile plan of Denoiser.denoise (DEN:661-669 == TMP:11-19), repaired per SURVEY App. D-2/D-3
+ * (integer origins, round-half-to-even, last tile clamped).  Pure integer host code.
+ * ys/xs must hold at least H/(crop-overlap)+1 and W/(crop-overlap)+1 ints. */
+int emd_plan_tiles(int H, int W, int crop, int overlap, int* ys, int* xs, int* ny, int* nx);
+
+/* Replaces preprocess (DMG:853-858) + scale0to1 (DEN:684-695 == DMG:817-828) on a whole image:
+ * NaN->0.5, Inf->0.5, then (x-min)/(max-min) in the input's precision (IEEE sub/div), constant
+ * image -> 0.5, result cast to f32.  in_f64 != 0: img is const double*. */
+int emd_normalise(emd_engine* e, const void* img, int in_f64, int H, int W, float* out, void* stream);
+
+/* Replaces the crop slicing of DEN:671-673: img [H,W] f32 -> crops [ny*nx,crop,crop] f32, row-major
+ * over (i,j) like the reference's double loop. */
+int emd_gather_crops(emd_engine* e, const float* img, int H, int W, const int* ys, const int* xs,
+                     int ny, int nx, int crop, float* crops, void* stream);
+
+/* Replaces the accumulate / contributions / divide / clip of DEN:658-659, 671-680 (repaired per
+ * App. D-4: +=): out[r,c] = sum of covering tiles / count, float64 like the reference's np.zeros
+ * accumulators; gather form (no atomics), stitch weights exact in binary FP. */
+int emd_stitch(emd_engine* e, const float* tiles, const int* ys, const int* xs, int ny, int nx,
+               int crop, int H, int W, int clip, double* out, void* stream);
+
+/* Replaces Denoiser.denoise (DEN:653-682 == TMP:3-32) end to end on one GPU: normalise -> tile ->
+ * batched forward -> overlap-averaged stitch -> clip.  img [H,W] f32 (or f64 with
+ * EMD_FLAG_INPUT_F64), out [H,W] f64. */
+int emd_denoise_image(emd_engine* e, const void* img, int H, int W, int overlap, int flags,
+                      int mode, double* out, void* stream);
+
+/* ---- parity / measurement hooks (no reference counterpart; used by tests and bench.py) ---- */
+
+/* keep != 0: every activation gets its own buffer (no reuse) so emd_get_activation works */
+int emd_set_keep_activations(emd_engine* e, int keep);
+/* copy a named activation of the last emd_forward to host as f32 NHWC; dims = {n,H,W,C} */
+int emd_get_activation(emd_engine* e, const char* name, float* out, size_t cap_elems, int dims[4]);
+/* run one fused layer on host NHWC f32 inputs (in2 = residual operand or NULL); out NHWC f32 */
+int emd_run_layer(emd_engine* e, const char* name, const float* in, const float* in2, int n,
+                  float* out, size_t out_cap_elems, int mode, int out_dims[4]);
+/* number of kernels this engine has launched since creation */
+long long emd_kernel_launches(const emd_engine* e);
+/* device time in ms of the kernels of the last emd_forward that belong to layer `name`
+ * (needs emd_set_profile(e,1); serialises the stream) */
+int emd_set_profile(emd_engine* e, int on);
+int emd_num_steps(const emd_engine* e);
+int emd_step_info(const emd_engine* e, int idx, char* name, size_t name_cap, float* ms,
+                  double* flops, double* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMD_H_ */

@@ -1,0 +1,211 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Tolerances (BASELINE.json north_star): relative L2 <= 1e-5 in the FP32 CUDA-core
+validation mode; tile indexing and stitch weights bit-exact.  16-bit tensor-core modes: see
+test_gpu_16bit.py."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+S = 64
+N = 2
+
+
+def layer_io_table():
+    """layer -> (input act, residual act or None, output act) in oracle activation names."""
+    t = {}
+    prev = "input"
+    for i in range(4):
+        t[f"cnn{i}"] = (prev, None, f"cnn{i}")
+        t[f"cnn{i}_last"] = (f"cnn{i}", None, f"cnn{i}_last")
+        t[f"residual{i}"] = (prev, None, f"residual{i}")
+        t[f"cnn{i}_strided"] = (f"cnn{i}_last", f"residual{i}", f"enc{i}")
+        prev = f"enc{i}"
+    trunk = "enc3"
+    for blk in range(-1, 11):
+        base = "cnn4_" if blk < 0 else f"mid{blk}_"
+        out = "trunk4" if blk < 0 else f"trunk_mid{blk}"
+        t[base + "0"] = (trunk, None, base + "0")
+        t[base + "1"] = (base + "0", None, base + "1")
+        t[base + "2"] = (base + "1", trunk, out)
+        trunk = out
+    for n in ("aspp_1x1", "aspp_r6", "aspp_r12", "aspp_r18", "aspp_image"):
+        t[n] = (trunk, None, n)
+    t["aspp_pellet"] = ("aspp_concat", None, "aspp_pellet")
+    t["upsample4"] = ("aspp_pellet", None, "upsample4")
+    t["deconv2_0"] = ("concat2", None, "deconv2_0")
+    t["residual2_d"] = ("concat2", None, "residual2_d")
+    t["deconv2_1"] = ("deconv2_0", "residual2_d", "dec2")
+    t["deconv2to1"] = ("dec2", None, "deconv2to1")
+    t["deconv1_0"] = ("concat1", None, "deconv1_0")
+    t["residual1_d"] = ("concat1", None, "residual1_d")
+    t["deconv1_1"] = ("deconv1_0", "residual1_d", "dec1")
+    t["deconv1to0"] = ("dec1", None, "deconv1to0")
+    t["deconv0_0"] = ("deconv1to0", None, "deconv0_0")
+    t["residual0_d"] = ("deconv1to0", None, "residual0_d")
+    t["deconv0_1"] = ("deconv0_0", "residual0_d", "dec0")
+    t["final"] = ("dec0", None, "output")
+    return t
+
+
+def oracle_acts(params, crops, dtype=torch.float64, **flags):
+    from oracle.net import OracleNet
+    net = OracleNet(params, crops.shape[-1], dtype=dtype)
+    net.collect = True
+    for k, v in flags.items():
+        setattr(net, k, v)
+    out = net.forward(crops)
+    a = net.acts
+    a["input"] = crops.reshape(crops.shape + (1,)).astype(np.float64)
+    a["aspp_concat"] = np.concatenate([a[k] for k in ("aspp_1x1", "aspp_r6", "aspp_r12", "aspp_r18", "aspp_image")], -1)
+    a["upsample4"] = a["concat2"][..., :256]
+    return out, a
+
+
+@pytest.fixture(scope="module")
+def setup(emd):
+    from oracle.weights import make_w0, make_w1
+    rng = np.random.default_rng(1234)
+    crops = rng.random((N, S, S)).astype(np.float32)
+    w1 = make_w1(crops, seed=0)
+    w0 = make_w0(0)
+    eng = emd.Engine(cropsize=S, max_batch=4)
+    return dict(emd=emd, eng=eng, crops=crops, w0=w0, w1=w1)
+
+
+def test_every_layer_fp32_within_1e5(setup):
+    """Each fused layer fed with the oracle's own O(1) input (W1 weights): isolates every layer."""
+    eng, emd = setup["eng"], setup["emd"]
+    eng.load_weights(emd.weights.pack(setup["w1"]))
+    _, acts = oracle_acts(setup["w1"], setup["crops"])
+    worst = ("", 0.0)
+    for layer, (i, r, o) in layer_io_table().items():
+        got = eng.run_layer(layer, acts[i], None if r is None else acts[r], mode="fp32")
+        assert got.shape == acts[o].shape, layer
+        err = rel_l2(got, acts[o])
+        worst = max(worst, (layer, err), key=lambda t: t[1])
+        assert err <= 1e-5, f"{layer}: rel-L2 {err:.3e}"
+    print("worst layer", worst)
+
+
+@pytest.mark.parametrize("wset", ["w0", "w1"])
+def test_network_fp32_end_to_end(setup, wset):
+    eng, emd = setup["eng"], setup["emd"]
+    eng.load_weights(emd.weights.pack(setup[wset]))
+    ref, acts = oracle_acts(setup[wset], setup["crops"])
+    eng.set_keep_activations(True)
+    out = eng.forward(setup["crops"], mode="fp32")
+    assert out.shape == ref.shape and out.dtype == np.float32
+    errs = {k: rel_l2(eng.activation(k), acts[k]) for k in ("enc0", "enc3", "trunk_mid10", "aspp_pellet", "dec2", "dec0")}
+    eng.set_keep_activations(False)
+    print(wset, "fp32 rel-L2 out", rel_l2(out, ref), errs)
+    assert rel_l2(out, ref) <= 1e-5
+    # buffer reuse must not change the result
+    np.testing.assert_array_equal(eng.forward(setup["crops"], mode="fp32"), out)
+
+
+def test_batch_chunking_and_device_pointers(setup):
+    """n > max_batch is processed in chunks; device tensors in/out give the same bits as host arrays."""
+    eng, emd = setup["eng"], setup["emd"]
+    eng.load_weights(emd.weights.pack(setup["w1"]))
+    rng = np.random.default_rng(5)
+    crops = rng.random((7, S, S)).astype(np.float32)
+    a = eng.forward(crops, mode="fp32")
+    b = np.concatenate([eng.forward(crops[i:i + 1], mode="fp32") for i in range(7)])
+    np.testing.assert_array_equal(a, b)
+    t = torch.from_numpy(crops).cuda()
+    c = eng.forward(t, mode="fp32")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(c.cpu().numpy(), a)
+    assert eng.kernel_launches > 0
+
+
+def test_forward_before_weights_is_an_error(emd):
+    eng = emd.Engine(cropsize=32, max_batch=1)
+    with pytest.raises(RuntimeError, match="emd_load_weights"):
+        eng.forward(np.zeros((1, 32, 32), np.float32), mode="fp32")
+    with pytest.raises(ValueError):
+        eng.forward(np.zeros((1, 16, 16), np.float32))
+
+
+# ---- wrapper: normalise / tile / stitch -----------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def weng(emd):
+    return emd.Engine(cropsize=64, max_batch=8)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_normalise_bit_exact(weng, dtype):
+    from oracle import wrapper as W
+    rng = np.random.default_rng(0)
+    img = (rng.random((301, 517)) * 1000 - 200).astype(dtype)
+    np.testing.assert_array_equal(weng.normalise(img), W.normalise(img))
+    img[5, 7] = np.nan; img[100, 3] = np.inf; img[200, 500] = -np.inf
+    np.testing.assert_array_equal(weng.normalise(img), W.normalise(img))
+    const = np.full((64, 64), 3.25, dtype)
+    assert (weng.normalise(const) == 0.5).all()
+    # NaN substitution participates in min/max: image in [10,20] with a NaN gets min 0.5
+    img2 = (rng.random((64, 64)) * 10 + 10).astype(dtype); img2[0, 0] = np.nan
+    np.testing.assert_array_equal(weng.normalise(img2), W.normalise(img2))
+
+
+def test_gather_and_stitch_bit_exact(weng):
+    from oracle import wrapper as W
+    rng = np.random.default_rng(1)
+    for H, Wd, crop, ov in [(150, 200, 64, 8), (64, 64, 64, 8), (333, 65, 64, 20), (600, 700, 512, 80)]:
+        img = rng.random((H, Wd)).astype(np.float32)
+        ys, xs = weng.plan_tiles(H, Wd, crop, ov)
+        assert ys == W.tile_origins(H, crop, ov) and xs == W.tile_origins(Wd, crop, ov)
+        crops = weng.gather_crops(img, ys, xs, crop)
+        ref_crops, _, _ = W.gather_crops(img, crop, ov)
+        np.testing.assert_array_equal(crops, ref_crops)
+        tiles = rng.random(crops.shape).astype(np.float32) * 1.5 - 0.2
+        for clip in (True, False):
+            got = weng.stitch(tiles, ys, xs, H, Wd, crop, clip)
+            assert got.dtype == np.float64
+            np.testing.assert_array_equal(got, W.stitch(tiles, ys, xs, H, Wd, crop, clip))
+        # identity network: overlap-averaging the image's own crops returns the image exactly,
+        # i.e. the stitch weights are exactly 1/count
+        np.testing.assert_array_equal(weng.stitch(crops, ys, xs, H, Wd, crop, False), img.astype(np.float64))
+
+
+def test_denoise_image_matches_oracle_pipeline(setup):
+    """Whole wrapper + network (FP32 mode) against the repaired reference pipeline on the CPU."""
+    from oracle import wrapper as W
+    from oracle.net import OracleNet
+    eng, emd = setup["eng"], setup["emd"]
+    eng.load_weights(emd.weights.pack(setup["w1"]))
+    rng = np.random.default_rng(9)
+    img = rng.poisson(rng.random((150, 130)) * 30).astype(np.float64)
+    img[3, 4] = np.nan
+    net = OracleNet(setup["w1"], S, dtype=torch.float64)
+    ref = W.denoise(img, net.forward, overlap=10, crop=S)
+    got = eng.denoise_image(img, overlap=10, mode="fp32")
+    assert got.shape == img.shape and got.dtype == np.float64
+    assert got.min() >= 0 and got.max() <= 1
+    assert rel_l2(got, ref) <= 1e-5
+    raw = eng.denoise_image(img.astype(np.float32), overlap=10, preprocess=False, postprocess=False, mode="fp32")
+    assert np.isnan(raw).any()  # preprocess=False passes the NaN through, like the reference would
+
+
+def test_denoiser_dropin_api(emd, setup):
+    """The reference's entry point: Denoiser(...).denoise(2-D float array) -> same-shape array in [0,1]."""
+    from oracle import wrapper as W
+    from oracle.net import OracleNet
+    d = emd.Denoiser(checkpoint_loc=setup["w1"], mode="fp32", cropsize=S, max_batch=4)
+    rng = np.random.default_rng(3)
+    img = rng.random((S, S))  # the reference's own smoke input: np.random.rand(512,512) (DEN:708), float64
+    out = d.denoise(img)
+    net = OracleNet(setup["w1"], S, dtype=torch.float64)
+    assert out.shape == img.shape and out.dtype == np.float64
+    assert rel_l2(out, W.denoise(img, net.forward, crop=S)) <= 1e-5
+    crop = d.denoise_crop(img.astype(np.float32))
+    assert crop.shape == (S, S) and 0 <= crop.min() and crop.max() <= 1
+    assert d.denoise_crop(img.astype(np.float32), postprocess=False).shape == (1, 1, S, S, 1)
+    assert d.preprocess(rng.random((100, 80)).astype(np.float32)).shape == (1, S, S, 1)
+    with pytest.raises(ValueError):
+        d.denoise(np.zeros((S - 1, S)))  # smaller than a crop
