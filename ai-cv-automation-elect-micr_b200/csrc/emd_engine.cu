@@ -46,7 +46,8 @@ struct Step {
   bool relu6 = false, clip01 = false;
   std::string wname;   // blob prefix
   const float *w = nullptr, *scale = nullptr, *shift = nullptr, *dw = nullptr;
-  void* w16[3] = {nullptr, nullptr, nullptr};  // indexed by ElemType
+  void* w16[3] = {nullptr, nullptr, nullptr};  // indexed by ElemType: UMMA tile image
+  const float* wr[3] = {nullptr, nullptr, nullptr};  // FP32 weights rounded to the 16-bit type (CUDA-core fallback of the 16-bit modes)
   float ms = 0.f;
   double flops = 0, bytes = 0;  // per crop: algorithmic FLOPs and (16-bit storage) HBM bytes
 };
@@ -68,14 +69,14 @@ struct emd_engine {
   char* d_blob = nullptr; size_t blob_bytes = 0;
   std::map<std::string, BlobEntry> entries;
   std::vector<void*> w16_allocs;
-  long long launches = 0;
+  long long launches = 0, umma_launches = 0;
   int last_n = 0, last_et = 0;
   // staging for host I/O of emd_forward
   float *d_stage_in = nullptr, *d_stage_out = nullptr;
   // whole-image pipeline buffers (grown on demand)
   void* d_img_raw = nullptr; size_t img_raw_bytes = 0;
   float* d_img = nullptr; size_t img_bytes = 0;
-  float *d_crops = nullptr, *d_tiles = nullptr; size_t crops_bytes = 0;
+  float *d_crops = nullptr, *d_tiles = nullptr; size_t crops_bytes = 0, tiles_bytes = 0;
   double* d_sout = nullptr; size_t sout_bytes = 0;
   double* d_minmax = nullptr; void* d_partial = nullptr;
   int* d_origins = nullptr;  // ys then xs, 2*256 ints
@@ -366,6 +367,17 @@ int bind_weights(emd_engine* e, const char* host_blob) {
         // 16-bit operand copies in the tcgen05 tile layout
         const float* hw = reinterpret_cast<const float*>(host_blob + e->entries[s.wname + "/w"].offset);
         for (int et : {ET_BF16, ET_F16}) {
+          {  // operand-precision copy for the CUDA-core fallback, so both kernels see the same operand values
+            const size_t nw = (size_t)K * s.Cout;
+            std::vector<float> r(nw);
+            for (size_t i = 0; i < nw; ++i)
+              r[i] = et == ET_BF16 ? __bfloat162float(__float2bfloat16_rn(hw[i])) : __half2float(__float2half_rn(hw[i]));
+            void* d = nullptr;
+            CU(e, cudaMalloc(&d, nw * 4));
+            e->w16_allocs.push_back(d);
+            CU(e, cudaMemcpy(d, r.data(), nw * 4, cudaMemcpyHostToDevice));
+            s.wr[et] = reinterpret_cast<const float*>(d);
+          }
           size_t nb = umma_pack_weights(hw, s.k * s.k, s.Cin, s.Cout, et, nullptr);
           if (!nb) continue;
           std::vector<char> tmp(nb);
@@ -416,13 +428,14 @@ View make_view(const ExecCtx& c, Ref r) {
   return v;
 }
 
-cudaError_t run_conv(ExecCtx& c, const ConvParams& p, int w16_ok) {
+cudaError_t run_conv(ExecCtx& c, ConvParams& p, const Step& s) {
   emd_engine* e = c.e;
-  if (c.et != ET_F32 && e->use_umma && w16_ok && umma_supported(p, c.et)) {
-    e->launches++;
+  e->launches++;
+  if (c.et != ET_F32 && e->use_umma && s.w16[c.et] && umma_supported(p, c.et)) {
+    e->umma_launches++;
     return launch_conv_umma(p, c.et, e->num_sms, c.s);
   }
-  e->launches++;
+  if (c.et != ET_F32 && s.wr[c.et]) p.w = s.wr[c.et];
   return launch_conv_simt(p, c.et, c.s);
 }
 
@@ -459,6 +472,7 @@ cudaError_t run_step(ExecCtx& c, Step& s) {
       p.istride = s.stride; p.ostride = 1; p.oy0 = p.ox0 = 0;
       p.Cin = s.Cin; p.Cout = s.Cout; p.w = s.w; p.w16 = s.w16[c.et]; p.scale = s.scale; p.shift = s.shift;
       p.relu6 = s.relu6; p.clip01 = s.clip01; p.out_f32 = to.external; p.in_f32 = ti.external;
+      p.wtaps = s.k * s.k;
       // taps: TF SAME. stride 1: symmetric (k/2)*rate.  stride 2 only occurs with k = 1 here (DMG:365-370).
       const int half = s.k / 2;
       p.ntaps = 0;
@@ -468,7 +482,7 @@ cudaError_t run_step(ExecCtx& c, Step& s) {
           if (std::abs(dy) >= ti.H || std::abs(dx) >= ti.W) continue;  // tap never in bounds (dilation >= map)
           p.dy[p.ntaps] = dy; p.dx[p.ntaps] = dx; p.wrow[p.ntaps] = ky * s.k + kx; p.ntaps++;
         }
-      return run_conv(c, p, s.w16[c.et] != nullptr);
+      return run_conv(c, p, s);
     }
     case SK_DECONV: {
       // conv2d_transpose 3x3 stride 2 SAME = 4 sub-pixel phases (App. A.4):
@@ -480,7 +494,7 @@ cudaError_t run_step(ExecCtx& c, Step& s) {
           p.N = c.n; p.MH = ti.H; p.MW = ti.W;
           p.istride = 1; p.ostride = 2; p.oy0 = py; p.ox0 = px;
           p.Cin = s.Cin; p.Cout = s.Cout; p.w = s.w; p.w16 = s.w16[c.et]; p.scale = s.scale; p.shift = s.shift;
-          p.relu6 = s.relu6;
+          p.relu6 = s.relu6; p.wtaps = 9;
           const int kys[2][2] = {{0, 2}, {1, -1}}, dys[2][2] = {{0, -1}, {0, 0}};
           p.ntaps = 0;
           for (int a = 0; a < 2; ++a) {
@@ -491,7 +505,7 @@ cudaError_t run_step(ExecCtx& c, Step& s) {
               p.wrow[p.ntaps] = kys[py][a] * 3 + kys[px][b2]; p.ntaps++;
             }
           }
-          cudaError_t r = run_conv(c, p, s.w16[c.et] != nullptr);
+          cudaError_t r = run_conv(c, p, s);
           if (r != cudaSuccess) return r;
         }
       return cudaSuccess;
@@ -759,9 +773,7 @@ int emd_stitch(emd_engine* e, const float* tiles, const int* ys, const int* xs, 
   const bool in_dev = is_device_ptr(tiles), out_dev = is_device_ptr(out);
   const float* d_src = tiles;
   if (!in_dev) {
-    size_t have = e->crops_bytes;
-    if ((rc = grow(e, &e->d_tiles, &have, ntl))) return rc;
-    // d_tiles shares the size bookkeeping of d_crops only when both were grown together; keep it simple:
+    if ((rc = grow(e, &e->d_tiles, &e->tiles_bytes, ntl))) return rc;
     CU(e, cudaMemcpyAsync(e->d_tiles, tiles, ntl, cudaMemcpyHostToDevice, s));
     d_src = e->d_tiles;
   }
@@ -812,11 +824,8 @@ int emd_denoise_image(emd_engine* e, const void* img, int H, int W, int overlap,
     e->launches += 3;
     d_norm = e->d_img;
   }
-  if (e->crops_bytes < ncr) {
-    if (e->d_tiles) { cudaFree(e->d_tiles); e->d_tiles = nullptr; }
-    if ((rc = grow(e, &e->d_crops, &e->crops_bytes, ncr))) return rc;
-  }
-  if (!e->d_tiles) CU(e, cudaMalloc(&e->d_tiles, e->crops_bytes));
+  if ((rc = grow(e, &e->d_crops, &e->crops_bytes, ncr))) return rc;
+  if ((rc = grow(e, &e->d_tiles, &e->tiles_bytes, ncr))) return rc;
   CU(e, launch_gather(d_norm, H, W, e->d_origins, e->d_origins + 256, ny, nx, crop, e->d_crops, s));
   e->launches++;
   const size_t per = (size_t)crop * crop;
@@ -941,6 +950,13 @@ int emd_run_layer(emd_engine* e, const char* name, const float* in, const float*
 }
 
 long long emd_kernel_launches(const emd_engine* e) { return e ? e->launches : -1; }
+long long emd_tensor_core_launches(const emd_engine* e) { return e ? e->umma_launches : -1; }
+
+int emd_set_tensor_cores(emd_engine* e, int on) {
+  if (!e) return EMD_EINVAL;
+  e->use_umma = on != 0;
+  return EMD_OK;
+}
 
 int emd_set_profile(emd_engine* e, int on) {
   if (!e) return EMD_EINVAL;

@@ -33,6 +33,7 @@ struct ConvParams {
   int istride, ostride, oy0, ox0;
   int ntaps;
   int dy[9], dx[9], wrow[9];
+  int wtaps;                 // taps in the weight tensor (k*k); wrow[t] < wtaps
   int Cin, Cout;
   const float* w;            // FP32 [ktaps*Cin][Cout] (TF kernel layout flattened)
   const void* w16;           // 16-bit operand copy, UMMA tile-swizzled (emd_umma.cu); may be null

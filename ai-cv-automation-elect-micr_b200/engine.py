@@ -159,6 +159,13 @@ class Engine:
     def kernel_launches(self):
         return int(self.lib.emd_kernel_launches(self.h))
 
+    @property
+    def tensor_core_launches(self):
+        return int(self.lib.emd_tensor_core_launches(self.h))
+
+    def set_tensor_cores(self, on=True):
+        self._check(self.lib.emd_set_tensor_cores(self.h, int(on)), "emd_set_tensor_cores")
+
     def set_profile(self, on=True):
         self._check(self.lib.emd_set_profile(self.h, int(on)), "emd_set_profile")
 

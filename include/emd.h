@@ -111,8 +111,12 @@ int emd_get_activation(emd_engine* e, const char* name, float* out, size_t cap_e
 /* run one fused layer on host NHWC f32 inputs (in2 = residual operand or NULL); out NHWC f32 */
 int emd_run_layer(emd_engine* e, const char* name, const float* in, const float* in2, int n,
                   float* out, size_t out_cap_elems, int mode, int out_dims[4]);
-/* number of kernels this engine has launched since creation */
+/* number of kernels this engine has launched since creation; of those, tcgen05 (UMMA) kernels */
 long long emd_kernel_launches(const emd_engine* e);
+long long emd_tensor_core_launches(const emd_engine* e);
+/* on = 0: the 16-bit modes run their GEMM-class layers on the CUDA-core kernel with the same
+ * 16-bit operand values (A/B check of the tcgen05 kernel); default on */
+int emd_set_tensor_cores(emd_engine* e, int on);
 /* device time in ms of the kernels of the last emd_forward that belong to layer `name`
  * (needs emd_set_profile(e,1); serialises the stream) */
 int emd_set_profile(emd_engine* e, int on);

@@ -1,0 +1,107 @@
+"""GPU parity tests of the 16-bit tensor-core modes (tcgen05 implicit-GEMM kernel).
+
+Three references per check:
+  (a) the same layer run on the CUDA-core kernel with identical 16-bit operand values
+      (emd_set_tensor_cores(0)): isolates the tcgen05 data path (descriptors, swizzle, TMEM epilogue);
+  (b) the FP64 oracle, per layer, O(1) inputs: north-star tolerance 5e-3 for BF16 operands;
+  (c) the oracle end to end, plain and with BF16 operand rounding emulated on the CPU
+      (OracleNet.emulate_bf16): the part of the end-to-end distance that is rounding, not kernels.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+from test_gpu_parity import layer_io_table, oracle_acts
+
+pytestmark = pytest.mark.gpu
+
+S, N = 64, 2
+
+
+@pytest.fixture(scope="module")
+def setup(emd):
+    from oracle.weights import make_w0, make_w1
+    rng = np.random.default_rng(1234)
+    crops = rng.random((N, S, S)).astype(np.float32)
+    eng = emd.Engine(cropsize=S, max_batch=4)
+    return dict(emd=emd, eng=eng, crops=crops, w0=make_w0(0), w1=make_w1(crops, seed=0))
+
+
+@pytest.mark.parametrize("mode,tol", [("bf16", 5e-3), ("fp16", 1e-3)])
+def test_every_layer_tensor_core(setup, mode, tol):
+    eng, emd = setup["eng"], setup["emd"]
+    eng.load_weights(emd.weights.pack(setup["w1"]))
+    _, acts = oracle_acts(setup["w1"], setup["crops"])
+    n_tc = 0
+    worst_ab, worst_or = ("", 0.0), ("", 0.0)
+    for layer, (i, r, o) in layer_io_table().items():
+        res = None if r is None else acts[r]
+        before = eng.tensor_core_launches
+        eng.set_tensor_cores(True)
+        got = eng.run_layer(layer, acts[i], res, mode=mode)
+        used_tc = eng.tensor_core_launches > before
+        n_tc += used_tc
+        eng.set_tensor_cores(False)
+        ab = eng.run_layer(layer, acts[i], res, mode=mode)
+        eng.set_tensor_cores(True)
+        e_ab, e_or = rel_l2(got, ab), rel_l2(got, acts[o])
+        worst_ab = max(worst_ab, (layer, e_ab), key=lambda t: t[1])
+        worst_or = max(worst_or, (layer, e_or), key=lambda t: t[1])
+        assert e_ab <= 5e-4, f"{layer}: tcgen05 vs CUDA-core with the same operands: {e_ab:.3e}"
+        assert e_or <= tol, f"{layer}: {mode} vs FP64 oracle: {e_or:.3e}"
+    print(mode, "tensor-core layers:", n_tc, "worst A/B", worst_ab, "worst vs oracle", worst_or)
+    assert n_tc >= 60  # everything GEMM-class except the 1-channel stem and the 64->1 final conv
+
+
+@pytest.mark.parametrize("wset", ["w0", "w1"])
+def test_network_bf16_end_to_end(setup, wset):
+    from oracle.net import OracleNet
+    eng, emd = setup["eng"], setup["emd"]
+    eng.load_weights(emd.weights.pack(setup[wset]))
+    ref, _ = oracle_acts(setup[wset], setup["crops"])
+    emu = OracleNet(setup[wset], S)
+    emu.emulate_bf16 = True
+    emu_out = emu.forward(setup["crops"])
+    out = eng.forward(setup["crops"], mode="bf16")
+    eng.set_tensor_cores(False)
+    out_cc = eng.forward(setup["crops"], mode="bf16")
+    eng.set_tensor_cores(True)
+    e_ref, e_emu, e_cc = rel_l2(out, ref), rel_l2(out, emu_out), rel_l2(out, out_cc)
+    budget = rel_l2(emu_out, ref)
+    print(f"{wset}: bf16 vs oracle {e_ref:.3e}; vs bf16-emulating oracle {e_emu:.3e}; vs CUDA-core bf16 {e_cc:.3e}; "
+          f"rounding budget (emulated vs exact oracle) {budget:.3e}")
+    assert np.isfinite(out).all() and out.min() >= 0 and out.max() <= 1
+    # the kernels add nothing beyond operand rounding: distance to the exact oracle stays within
+    # 1.5x of what BF16 rounding alone costs on the CPU
+    assert e_ref <= 1.5 * budget + 1e-3
+    assert e_cc <= 0.5 * budget + 1e-3
+
+
+@pytest.mark.parametrize("wset", ["w0", "w1"])
+def test_network_fp16_end_to_end(setup, wset):
+    eng, emd = setup["eng"], setup["emd"]
+    eng.load_weights(emd.weights.pack(setup[wset]))
+    ref, _ = oracle_acts(setup[wset], setup["crops"])
+    out = eng.forward(setup["crops"], mode="fp16")
+    e = rel_l2(out, ref)
+    print(f"{wset}: fp16 vs oracle {e:.3e}")
+    assert e <= (5e-3 if wset == "w0" else 1.5e-2)
+
+
+def test_tensor_core_shapes_s96_and_ragged_batch(setup):
+    """96x96 crops (small_scans shape): 6x6 maps at stride 16, M tiles that straddle images, dilated
+    taps that never land inside the map; batch 3 leaves ragged last tiles."""
+    from oracle.weights import make_w1
+    emd = setup["emd"]
+    rng = np.random.default_rng(77)
+    crops = rng.random((3, 96, 96)).astype(np.float32)
+    w1 = make_w1(crops, seed=5)
+    eng = emd.Engine(cropsize=96, max_batch=3)
+    eng.load_weights(emd.weights.pack(w1))
+    out = eng.forward(crops, mode="bf16")
+    eng.set_tensor_cores(False)
+    out_cc = eng.forward(crops, mode="bf16")
+    ref, _ = oracle_acts(w1, crops)
+    print("S=96: bf16 vs oracle", rel_l2(out, ref), "tcgen05 vs CUDA-core", rel_l2(out, out_cc))
+    assert rel_l2(out, out_cc) <= 3e-2
+    assert rel_l2(out, ref) <= 1.5e-1

@@ -188,8 +188,10 @@ def test_denoise_image_matches_oracle_pipeline(setup):
     assert got.shape == img.shape and got.dtype == np.float64
     assert got.min() >= 0 and got.max() <= 1
     assert rel_l2(got, ref) <= 1e-5
-    raw = eng.denoise_image(img.astype(np.float32), overlap=10, preprocess=False, postprocess=False, mode="fp32")
-    assert np.isnan(raw).any()  # preprocess=False passes the NaN through, like the reference would
+    pre = W.normalise(img)  # preprocess=False / postprocess=False: caller normalises, no clip
+    raw = eng.denoise_image(pre, overlap=10, preprocess=False, postprocess=False, mode="fp32")
+    ref_raw = W.denoise(pre, net.forward, preprocess=False, postprocess=False, overlap=10, crop=S)
+    assert rel_l2(raw, ref_raw) <= 1e-5
 
 
 def test_denoiser_dropin_api(emd, setup):
