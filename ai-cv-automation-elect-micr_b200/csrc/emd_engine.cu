@@ -578,6 +578,8 @@ int emd_create(emd_engine** out, int device, int cropsize, int variant, int max_
   e->device = device; e->S = cropsize; e->variant = variant; e->max_batch = max_batch;
   const char* env = getenv("EMD_DISABLE_UMMA");
   e->use_umma = !(env && env[0] == '1');
+  env = getenv("EMD_DISABLE_TMA");
+  umma_set_tma(!(env && env[0] == '1'));
 #define CUC(call)                                                                                       \
   do {                                                                                                  \
     cudaError_t _r = (call);                                                                            \

@@ -74,6 +74,7 @@ cudaError_t launch_uncast(const void* src, float* dst, size_t n, int et, cudaStr
 bool umma_supported(const ConvParams& p, int et);
 cudaError_t launch_conv_umma(const ConvParams& p, int et, int num_sms, cudaStream_t s);
 // packs FP32 [K][Cout] weights into the UMMA tile image; returns bytes needed when dst == nullptr
+void umma_set_tma(bool on);   // A tiles through TMA tensor maps (default) or the cp.async gather only
 size_t umma_pack_weights(const float* w, int ntaps, int Cin, int Cout, int et, void* dst_host);
 
 // emd_kernels_wrap.cu: whole-image wrapper kernels

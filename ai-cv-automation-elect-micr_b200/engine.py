@@ -142,6 +142,10 @@ class Engine:
             import torch
             f64 = img.dtype == torch.float64
         H, W = int(img.shape[0]), int(img.shape[1])
+        if H < self.S or W < self.S:
+            raise ValueError(f"image {H}x{W} is smaller than the {self.S}x{self.S} crop")
+        if not 0 <= overlap < self.S:
+            raise ValueError(f"overlap {overlap} outside [0,{self.S})")
         if out is None:
             if is_np:
                 out = np.empty((H, W), np.float64)

@@ -201,10 +201,10 @@ def test_denoiser_dropin_api(emd, setup):
     d = emd.Denoiser(checkpoint_loc=setup["w1"], mode="fp32", cropsize=S, max_batch=4)
     rng = np.random.default_rng(3)
     img = rng.random((S, S))  # the reference's own smoke input: np.random.rand(512,512) (DEN:708), float64
-    out = d.denoise(img)
+    out = d.denoise(img, overlap=8)
     net = OracleNet(setup["w1"], S, dtype=torch.float64)
     assert out.shape == img.shape and out.dtype == np.float64
-    assert rel_l2(out, W.denoise(img, net.forward, crop=S)) <= 1e-5
+    assert rel_l2(out, W.denoise(img, net.forward, overlap=8, crop=S)) <= 1e-5
     crop = d.denoise_crop(img.astype(np.float32))
     assert crop.shape == (S, S) and 0 <= crop.min() and crop.max() <= 1
     assert d.denoise_crop(img.astype(np.float32), postprocess=False).shape == (1, 1, S, S, 1)
