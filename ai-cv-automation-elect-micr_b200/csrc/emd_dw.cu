@@ -1,0 +1,198 @@
+// emd_dw.cu -- depthwise 3x3 convolution (stride 1, rate 1) for the 16-bit modes, TMA-fed.
+//
+// The DepthwiseConv2dNative half of slim.separable_convolution2d (DMG:253-273) is memory-bound
+// (9 MACs per element).  One persistent CTA walks (8 x 16 pixel tile, 64-channel chunk) items:
+//   producer warp : one 4-D TMA load per item brings the 10 x 18 pixel halo of the chunk into shared
+//                   memory (zero fill outside the image = SAME padding), 3-deep mbarrier ring
+//   8 math warps  : thread = (8 channels, one pixel column, 4 output rows); the 3x3 window slides
+//                   down the column in registers (FP32 accumulate), each quarter-warp reads one
+//                   full 128-byte pixel row per LDS.128 and writes one full 128-byte segment per STG.128
+#include "emd_kernels.h"
+#include "emd_tma.h"
+
+namespace emd {
+namespace {
+
+constexpr int kTH = 8, kTW = 16, kHaloH = kTH + 2, kHaloW = kTW + 2;
+constexpr int kChunk = 64;
+constexpr int kStageBytes = kHaloH * kHaloW * kChunk * 2;  // 23040
+constexpr int kStages = 4;
+constexpr int kMathThreads = 256;
+
+struct DwTmaArgs {
+  DwParams p;
+  int tiles_x, tiles_per_img, nchunks, items;
+};
+
+template <typename T> struct Up;
+template <> struct Up<__nv_bfloat16> {
+  static __device__ __forceinline__ void up8(const uint4& u, float* f) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+};
+template <> struct Up<__half> {
+  static __device__ __forceinline__ void up8(const uint4& u, float* f) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    }
+  }
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kMathThreads + 32, 1) dw_tma_kernel(const __grid_constant__ DwTmaArgs a,
+                                                                      const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 127u) & ~127u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  const uint32_t bar_full = ptx::smem_u32(bars), bar_empty = bar_full + 8u * kStages;
+  const DwParams& p = a.p;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(bar_full + 8u * s, 1); ptx::mbar_init(bar_empty + 8u * s, kMathThreads); }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&tmap);
+  }
+  __syncthreads();
+
+  if (threadIdx.x >= kMathThreads) {
+    // ---------------- producer ----------------
+    if (threadIdx.x == kMathThreads) {
+      int it = 0;
+      for (int item = blockIdx.x; item < a.items; item += gridDim.x, ++it) {
+        const int tile = item / a.nchunks, c = item - tile * a.nchunks;
+        const int n_img = tile / a.tiles_per_img;
+        const int rem = tile - n_img * a.tiles_per_img;
+        const int by = rem / a.tiles_x, bx = rem - by * a.tiles_x;
+        const int s = it % kStages;
+        ptx::mbar_wait(bar_empty + 8u * s, (uint32_t)(((it / kStages) & 1) ^ 1));
+        ptx::mbar_arrive_expect_tx(bar_full + 8u * s, kStageBytes);
+        ptx::tma_load_4d(base + (uint32_t)s * kStageBytes, &tmap, c * kChunk, bx * kTW - 1, by * kTH - 1, n_img, bar_full + 8u * s);
+      }
+    }
+    return;
+  }
+
+  // ---------------- math warps ----------------
+  const int tid = threadIdx.x;
+  const int q = tid & 7, col = (tid >> 3) & 15, half = tid >> 7;
+  int it = 0;
+  int cur_c = -1;
+  float w[9][8];
+  for (int item = blockIdx.x; item < a.items; item += gridDim.x, ++it) {
+    const int tile = item / a.nchunks, c = item - tile * a.nchunks;
+    const int n_img = tile / a.tiles_per_img;
+    const int rem = tile - n_img * a.tiles_per_img;
+    const int by = rem / a.tiles_x, bx = rem - by * a.tiles_x;
+    const int ch = c * kChunk + q * 8;
+    const bool ch_ok = ch < p.in.C;
+    if (c != cur_c) {  // this thread's 9 x 8 depthwise weights for the chunk
+      cur_c = c;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+        if (ch_ok) {
+          w0 = __ldg(reinterpret_cast<const float4*>(p.w + t * p.in.C + ch));
+          w1 = __ldg(reinterpret_cast<const float4*>(p.w + t * p.in.C + ch + 4));
+        }
+        w[t][0] = w0.x; w[t][1] = w0.y; w[t][2] = w0.z; w[t][3] = w0.w;
+        w[t][4] = w1.x; w[t][5] = w1.y; w[t][6] = w1.z; w[t][7] = w1.w;
+      }
+    }
+    const int s = it % kStages;
+    ptx::mbar_wait(bar_full + 8u * s, (uint32_t)((it / kStages) & 1));
+    const uint8_t* hb = smem + (size_t)s * kStageBytes + q * 16;
+    // window rows: halo rows (4*half + i + ky), columns col..col+2
+    float win[3][3][8];
+    auto load_row = [&](int hy, float (&dst)[3][8]) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const uint4 u = *reinterpret_cast<const uint4*>(hb + (size_t)(hy * kHaloW + col + kx) * (kChunk * 2));
+        Up<T>::up8(u, dst[kx]);
+      }
+    };
+    load_row(4 * half + 0, win[0]);
+    load_row(4 * half + 1, win[1]);
+    T* obase = reinterpret_cast<T*>(p.out.ptr) +
+               (((size_t)n_img * p.out.H + by * kTH + 4 * half) * p.out.W + bx * kTW + col) * p.out.pitch + p.out.coff + ch;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      load_row(4 * half + i + 2, win[(i + 2) % 3]);
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(win[(i + ky) % 3][kx][j], w[ky * 3 + kx][j], acc[j]);
+      if (ch_ok) {
+        uint4 o;
+        o.x = Up<T>::pack(acc[0], acc[1]); o.y = Up<T>::pack(acc[2], acc[3]);
+        o.z = Up<T>::pack(acc[4], acc[5]); o.w = Up<T>::pack(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(obase + (size_t)i * p.out.W * p.out.pitch) = o;
+      }
+    }
+    ptx::mbar_arrive(bar_empty + 8u * s);
+  }
+}
+
+}  // namespace
+
+bool dw_tma_supported(const DwParams& p, int et) {
+  if (et != ET_BF16 && et != ET_F16) return false;
+  if (p.in_f32 || p.stride != 1 || p.rate != 1 || p.pad != 1) return false;
+  if (p.OH % kTH || p.OW % kTW) return false;
+  if ((p.in.C & 7) || (p.in.pitch & 7) || (p.in.coff & 7) || (p.out.pitch & 7) || (p.out.coff & 7)) return false;
+  return tma_encoder() != nullptr;
+}
+
+cudaError_t launch_dw_tma(const DwParams& p, int et, int num_sms, cudaStream_t s) {
+  DwTmaArgs a;
+  a.p = p;
+  a.tiles_x = p.OW / kTW;
+  a.tiles_per_img = (p.OH / kTH) * a.tiles_x;
+  a.nchunks = (p.in.C + kChunk - 1) / kChunk;
+  a.items = p.N * a.tiles_per_img * a.nchunks;
+  CUtensorMap tmap;
+  void* base = reinterpret_cast<char*>(p.in.ptr) + (size_t)p.in.coff * 2;
+  if (!tma_encode_nhwc(&tmap, et == ET_BF16, base, p.in.C, p.in.W, p.in.H, p.N, p.in.pitch, kChunk, kHaloW, kHaloH, 1, false))
+    return cudaErrorInvalidValue;
+  const size_t smem = 128 + (size_t)kStages * kStageBytes + 2 * kStages * 8;
+  const int grid = a.items < num_sms ? a.items : num_sms;
+  static thread_local int attr_dev[2] = {-1, -1};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (et == ET_BF16) {
+    if (attr_dev[0] != dev) {
+      cudaError_t r = cudaFuncSetAttribute(dw_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (r != cudaSuccess) return r;
+      attr_dev[0] = dev;
+    }
+    dw_tma_kernel<__nv_bfloat16><<<grid, kMathThreads + 32, smem, s>>>(a, tmap);
+  } else {
+    if (attr_dev[1] != dev) {
+      cudaError_t r = cudaFuncSetAttribute(dw_tma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (r != cudaSuccess) return r;
+      attr_dev[1] = dev;
+    }
+    dw_tma_kernel<__half><<<grid, kMathThreads + 32, smem, s>>>(a, tmap);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace emd

@@ -451,6 +451,7 @@ cudaError_t run_step(ExecCtx& c, Step& s) {
       p.pad = (s.stride == 1) ? s.rate : 0;  // TF SAME: symmetric `rate` at stride 1; 0 before / 1 after at stride 2 on even sizes
       p.w = s.dw; p.in_f32 = ti.external;
       e->launches++;
+      if (e->use_umma && dw_tma_supported(p, c.et)) return launch_dw_tma(p, c.et, e->num_sms, c.s);
       return launch_dw3x3(p, c.et, c.s);
     }
     case SK_POOL: {

@@ -70,6 +70,10 @@ cudaError_t launch_avgpool(const PoolParams& p, int et, cudaStream_t s);
 cudaError_t launch_cast(const float* src, void* dst, size_t n, int et, cudaStream_t s);
 cudaError_t launch_uncast(const void* src, float* dst, size_t n, int et, cudaStream_t s);
 
+// emd_dw.cu: TMA-fed depthwise 3x3 (stride 1) for the 16-bit modes
+bool dw_tma_supported(const DwParams& p, int et);
+cudaError_t launch_dw_tma(const DwParams& p, int et, int num_sms, cudaStream_t s);
+
 // emd_umma.cu: tcgen05 implicit GEMM (16-bit element types only)
 bool umma_supported(const ConvParams& p, int et);
 cudaError_t launch_conv_umma(const ConvParams& p, int et, int num_sms, cudaStream_t s);

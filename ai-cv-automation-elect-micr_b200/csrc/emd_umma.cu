@@ -369,6 +369,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       const bool valid = row_coords(a, mt, row, n_img, y, x);
       unsigned pix = 0;
       if (valid) pix = (unsigned)((n_img * p.out.H + y * p.ostride + p.oy0) * p.out.W + x * p.ostride + p.ox0);
+      // coalesced-phase geometry: lane -> (pixel 8*itr + lane/4, channels 8*(lane%4) .. +8) of each 32-column group
+      const int sub = lane & 3;
+      unsigned ppix[4];
+      bool pvalid[4];
+#pragma unroll
+      for (int itr = 0; itr < 4; ++itr) {
+        const int pr = itr * 8 + (lane >> 2);
+        ppix[itr] = __shfl_sync(0xffffffffu, pix, pr);
+        pvalid[itr] = __shfl_sync(0xffffffffu, (int)valid, pr) != 0;
+      }
+      // residual operand: prefetched one 32-column group ahead (the first group before the accumulator is awaited)
+      const T* resp = reinterpret_cast<const T*>(p.res.ptr);
+      uint4 rnext[4];
+      auto load_res = [&](int c0, uint4 (&r)[4]) {
+        const int cgl = n0 + c0 + 8 * sub;
+#pragma unroll
+        for (int itr = 0; itr < 4; ++itr) {
+          r[itr] = make_uint4(0u, 0u, 0u, 0u);
+          if (resp && pvalid[itr] && c0 + 8 * sub < n && cgl < p.Cout)
+            r[itr] = *reinterpret_cast<const uint4*>(resp + (size_t)ppix[itr] * p.res.pitch + p.res.coff + cgl);
+        }
+      };
+      if (!narrow) load_res(0, rnext);
       const int acc = tcount & 1;
       const uint32_t acc_ph = (uint32_t)((tcount >> 1) & 1);
       mbar_wait(bar_tfull + 8u * acc, acc_ph);
@@ -395,6 +418,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       } else {
         for (int c0 = 0; c0 < n; c0 += 32) {
           const int ncol = min(32, n - c0);   // 16 or 32 (n is a multiple of 16)
+          uint4 rcur[4];
+#pragma unroll
+          for (int itr = 0; itr < 4; ++itr) rcur[itr] = rnext[itr];
+          if (c0 + 32 < n) load_res(c0 + 32, rnext);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (h * 16 < ncol) {
@@ -419,22 +446,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             }
           }
           __syncwarp();
-          // coalesced phase: lane -> (pixel 8*itr + lane/4, channels 8*(lane%4) .. +8)
-          const int sub = lane & 3;
           const int cg = n0 + c0 + 8 * sub;
 #pragma unroll
           for (int itr = 0; itr < 4; ++itr) {
             const int pr = itr * 8 + (lane >> 2);
-            const unsigned ppix = __shfl_sync(0xffffffffu, pix, pr);
-            const int pvalid = __shfl_sync(0xffffffffu, (int)valid, pr);
-            if (pvalid && 8 * sub < ncol && cg < p.Cout) {
+            if (pvalid[itr] && 8 * sub < ncol && cg < p.Cout) {
               const float4 f0 = *reinterpret_cast<const float4*>(stg + pr * 32 + (((2 * sub) ^ (pr & 7)) << 2));
               const float4 f1 = *reinterpret_cast<const float4*>(stg + pr * 32 + (((2 * sub + 1) ^ (pr & 7)) << 2));
               float yv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-              if (p.res.ptr) {
-                const uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.res.ptr) +
-                                                                (size_t)ppix * p.res.pitch + p.res.coff + cg);
-                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+              if (resp) {
+                const uint32_t rw[4] = {rcur[itr].x, rcur[itr].y, rcur[itr].z, rcur[itr].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float2 f = Cvt<T>::unpack(rw[j]);
@@ -444,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
               uint4 o;
               o.x = Cvt<T>::pack(yv[0], yv[1]); o.y = Cvt<T>::pack(yv[2], yv[3]);
               o.z = Cvt<T>::pack(yv[4], yv[5]); o.w = Cvt<T>::pack(yv[6], yv[7]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.out.ptr) + (size_t)ppix * p.out.pitch + p.out.coff + cg) = o;
+              *reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.out.ptr) + (size_t)ppix[itr] * p.out.pitch + p.out.coff + cg) = o;
             }
           }
           __syncwarp();

@@ -264,8 +264,22 @@ def main():
         roof["kernel_ms"] = kms
         roof["kernel_share_of_step"] = kms / tot_ms
         roof["peak_source"] = pk["source"]
-        # whole-network roofline: sum over steps of max(FLOPs/P_tensor, bytes/BW_hbm), per batch
-        t_roof = sum(max(i[2] * B / (pk["tflops"] * 1e12), i[3] * B / (pk["hbm_gbs"] * 1e9)) for i in info)
+        # whole-network roofline with per-layer fusion: sum over layers of
+        # max(FLOPs/P_tensor, bytes/BW_hbm); a separable block counts as ONE unit whose depthwise
+        # intermediate never leaves the SM (its write + re-read are not algorithmic bytes)
+        def fused_units(steps):
+            units, k = [], 0
+            while k < len(steps):
+                n, _, fl, by = steps[k]
+                if n.endswith(":dw") and k + 1 < len(steps) and steps[k + 1][0] == n[:-3]:
+                    mid = by / 5.0 if n[:-3].endswith("_strided") else by / 2.0   # bytes of the dw output
+                    units.append((fl + steps[k + 1][2], by - mid + steps[k + 1][3] - mid))
+                    k += 2
+                else:
+                    units.append((fl, by))
+                    k += 1
+            return units
+        t_roof = sum(max(fl * B / (pk["tflops"] * 1e12), by * B / (pk["hbm_gbs"] * 1e9)) for fl, by in fused_units(info))
         roof["network_roofline_ms"] = t_roof * 1e3
         roof["network_frac"] = t_roof * 1e3 / (ms / args.steps)
         top = sorted(info, key=lambda i: -i[1])[:8]
