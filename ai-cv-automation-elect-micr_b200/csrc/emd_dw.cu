@@ -22,6 +22,10 @@ constexpr int kMathThreads = 256;
 struct DwTmaArgs {
   DwParams p;
   int tiles_x, tiles_per_img, nchunks, items;
+  // kReduce (final 3x3 conv 64 -> 1, DMG:531-538): p.w holds the [9][64] kernel, the 64 products are
+  // summed over channels, then scale/shift, ReLU6, clip and an FP32 store
+  float scale, shift;
+  int relu6, clip01;
 };
 
 template <typename T> struct Up;
@@ -51,7 +55,7 @@ template <> struct Up<__half> {
   }
 };
 
-template <typename T>
+template <typename T, bool kReduce>
 __global__ void __launch_bounds__(kMathThreads + 32, 1) dw_tma_kernel(const __grid_constant__ DwTmaArgs a,
                                                                       const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ uint8_t smem_raw[];
@@ -140,7 +144,18 @@ __global__ void __launch_bounds__(kMathThreads + 32, 1) dw_tma_kernel(const __gr
         for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = fmaf(win[(i + ky) % 3][kx][j], w[ky * 3 + kx][j], acc[j]);
-      if (ch_ok) {
+      if (kReduce) {
+        float t = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 4);   // the 8 lanes of a quarter-warp hold the 8 channel chunks
+        if (q == 0) {
+          float v = fmaf(t, a.scale, a.shift);
+          if (a.relu6) v = fminf(fmaxf(v, 0.f), 6.f);
+          if (a.clip01) v = fminf(fmaxf(v, 0.f), 1.f);
+          reinterpret_cast<float*>(p.out.ptr)[((size_t)n_img * p.out.H + by * kTH + 4 * half + i) * p.out.W + bx * kTW + col] = v;
+        }
+      } else if (ch_ok) {
         uint4 o;
         o.x = Up<T>::pack(acc[0], acc[1]); o.y = Up<T>::pack(acc[2], acc[3]);
         o.z = Up<T>::pack(acc[4], acc[5]); o.w = Up<T>::pack(acc[6], acc[7]);
@@ -161,9 +176,22 @@ bool dw_tma_supported(const DwParams& p, int et) {
   return tma_encoder() != nullptr;
 }
 
-cudaError_t launch_dw_tma(const DwParams& p, int et, int num_sms, cudaStream_t s) {
-  DwTmaArgs a;
-  a.p = p;
+template <typename T, bool kReduce>
+static cudaError_t launch_t(const DwTmaArgs& a, const CUtensorMap& tmap, int grid, size_t smem, cudaStream_t s) {
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr_dev != dev) {
+    cudaError_t r = cudaFuncSetAttribute(dw_tma_kernel<T, kReduce>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (r != cudaSuccess) return r;
+    attr_dev = dev;
+  }
+  dw_tma_kernel<T, kReduce><<<grid, kMathThreads + 32, smem, s>>>(a, tmap);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_common(DwTmaArgs& a, int et, bool reduce, int num_sms, cudaStream_t s) {
+  const DwParams& p = a.p;
   a.tiles_x = p.OW / kTW;
   a.tiles_per_img = (p.OH / kTH) * a.tiles_x;
   a.nchunks = (p.in.C + kChunk - 1) / kChunk;
@@ -174,25 +202,37 @@ cudaError_t launch_dw_tma(const DwParams& p, int et, int num_sms, cudaStream_t s
     return cudaErrorInvalidValue;
   const size_t smem = 128 + (size_t)kStages * kStageBytes + 2 * kStages * 8;
   const int grid = a.items < num_sms ? a.items : num_sms;
-  static thread_local int attr_dev[2] = {-1, -1};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (et == ET_BF16) {
-    if (attr_dev[0] != dev) {
-      cudaError_t r = cudaFuncSetAttribute(dw_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (r != cudaSuccess) return r;
-      attr_dev[0] = dev;
-    }
-    dw_tma_kernel<__nv_bfloat16><<<grid, kMathThreads + 32, smem, s>>>(a, tmap);
-  } else {
-    if (attr_dev[1] != dev) {
-      cudaError_t r = cudaFuncSetAttribute(dw_tma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (r != cudaSuccess) return r;
-      attr_dev[1] = dev;
-    }
-    dw_tma_kernel<__half><<<grid, kMathThreads + 32, smem, s>>>(a, tmap);
-  }
-  return cudaGetLastError();
+  if (et == ET_BF16)
+    return reduce ? launch_t<__nv_bfloat16, true>(a, tmap, grid, smem, s) : launch_t<__nv_bfloat16, false>(a, tmap, grid, smem, s);
+  return reduce ? launch_t<__half, true>(a, tmap, grid, smem, s) : launch_t<__half, false>(a, tmap, grid, smem, s);
+}
+
+cudaError_t launch_dw_tma(const DwParams& p, int et, int num_sms, cudaStream_t s) {
+  DwTmaArgs a;
+  a.p = p; a.scale = 1.f; a.shift = 0.f; a.relu6 = a.clip01 = 0;
+  return launch_common(a, et, false, num_sms, s);
+}
+
+// final 3x3 conv 64 -> 1 (conv_block_not_sep(deconv0, 1), DMG:531) + clip (DMG:534-538) as a channel-reducing
+// depthwise pass; only taken when the conv is exactly that shape
+bool final_tma_supported(const ConvParams& p, int et) {
+  if (et != ET_BF16 && et != ET_F16) return false;
+  if (p.Cout != 1 || p.Cin != 64 || p.ntaps != 9 || p.wtaps != 9 || p.istride != 1 || p.ostride != 1 || !p.out_f32 || p.in_f32) return false;
+  for (int t = 0; t < 9; ++t)
+    if (p.dy[t] != t / 3 - 1 || p.dx[t] != t % 3 - 1 || p.wrow[t] != t) return false;
+  if (p.MH % kTH || p.MW % kTW || (p.in.pitch & 7) || (p.in.coff & 7) || p.res.ptr) return false;
+  if (p.out.pitch != 1 || p.out.coff != 0) return false;
+  return tma_encoder() != nullptr;
+}
+
+cudaError_t launch_final_tma(const ConvParams& c, float scale, float shift, int et, int num_sms, cudaStream_t s) {
+  DwTmaArgs a;
+  DwParams& p = a.p;
+  p.in = c.in; p.out = c.out; p.N = c.N; p.OH = c.MH; p.OW = c.MW; p.stride = 1; p.rate = 1; p.pad = 1;
+  p.w = c.w;   // FP32 [9*64][1] == [9][64]
+  p.in_f32 = 0;
+  a.scale = scale; a.shift = shift; a.relu6 = c.relu6; a.clip01 = c.clip01;
+  return launch_common(a, et, true, num_sms, s);
 }
 
 }  // namespace emd

@@ -48,6 +48,7 @@ struct Step {
   const float *w = nullptr, *scale = nullptr, *shift = nullptr, *dw = nullptr;
   void* w16[3] = {nullptr, nullptr, nullptr};  // indexed by ElemType: UMMA tile image
   const float* wr[3] = {nullptr, nullptr, nullptr};  // FP32 weights rounded to the 16-bit type (CUDA-core fallback of the 16-bit modes)
+  float scale0 = 1.f, shift0 = 0.f;  // host copies of scale[0] / shift[0] (single-output-channel layers)
   float ms = 0.f;
   double flops = 0, bytes = 0;  // per crop: algorithmic FLOPs and (16-bit storage) HBM bytes
 };
@@ -364,6 +365,8 @@ int bind_weights(emd_engine* e, const char* host_blob) {
               !(s.shift = entry_ptr(e, "aspp_image/bias", 1, s.Cout, &why)))
             return fail(e, EMD_EINVAL, "%s", why.c_str());
         }
+        s.scale0 = *reinterpret_cast<const float*>(host_blob + e->entries[s.wname + "/scale"].offset);
+        s.shift0 = *reinterpret_cast<const float*>(host_blob + e->entries[s.wname + "/shift"].offset);
         // 16-bit operand copies in the tcgen05 tile layout
         const float* hw = reinterpret_cast<const float*>(host_blob + e->entries[s.wname + "/w"].offset);
         for (int et : {ET_BF16, ET_F16}) {
@@ -431,6 +434,10 @@ View make_view(const ExecCtx& c, Ref r) {
 cudaError_t run_conv(ExecCtx& c, ConvParams& p, const Step& s) {
   emd_engine* e = c.e;
   e->launches++;
+  if (c.et != ET_F32 && e->use_umma && final_tma_supported(p, c.et)) {
+    p.w = s.wr[c.et];
+    return launch_final_tma(p, s.scale0, s.shift0, c.et, e->num_sms, c.s);
+  }
   if (c.et != ET_F32 && e->use_umma && s.w16[c.et] && umma_supported(p, c.et)) {
     e->umma_launches++;
     return launch_conv_umma(p, c.et, e->num_sms, c.s);
@@ -439,12 +446,14 @@ cudaError_t run_conv(ExecCtx& c, ConvParams& p, const Step& s) {
   return launch_conv_simt(p, c.et, c.s);
 }
 
-cudaError_t run_step(ExecCtx& c, Step& s) {
+cudaError_t run_step(ExecCtx& c, int idx) {
   emd_engine* e = c.e;
+  Step& s = e->steps[idx];
   const Tensor& ti = e->tensors[s.in.t];
   const Tensor& to = e->tensors[s.out.t];
   switch (s.kind) {
     case SK_DW: {
+      if (s.Cin == 1) return cudaSuccess;  // 1-channel stem: the depthwise is fused into the pointwise kernel below
       DwParams p{};
       p.in = make_view(c, s.in); p.out = make_view(c, s.out);
       p.N = c.n; p.OH = to.H; p.OW = to.W; p.stride = s.stride; p.rate = s.rate;
@@ -466,6 +475,22 @@ cudaError_t run_step(ExecCtx& c, Step& s) {
       return launch_resize(p, c.et, c.s);
     }
     case SK_CONV: {
+      if (s.Cin == 1 && s.k == 1) {  // network stem (cnn0 / residual0): outer-product kernel on the FP32 input
+        const Step* dws = (idx > 0 && e->steps[idx - 1].kind == SK_DW && e->steps[idx - 1].layer == s.layer) ? &e->steps[idx - 1] : nullptr;
+        const Ref rin = dws ? dws->in : s.in;
+        const Tensor& tin = e->tensors[rin.t];
+        if (tin.external && !(s.Cout & 7)) {
+          StemParams p{};
+          View vin = make_view(c, rin);
+          p.in = reinterpret_cast<const float*>(vin.ptr); p.IH = tin.H; p.IW = tin.W;
+          p.out = make_view(c, s.out); p.N = c.n;
+          p.dw = dws ? dws->dw : nullptr;
+          p.w = (c.et != ET_F32 && s.wr[c.et]) ? s.wr[c.et] : s.w;
+          p.scale = s.scale; p.shift = s.shift; p.istride = s.stride; p.relu6 = s.relu6;
+          e->launches++;
+          return launch_stem(p, c.et, c.s);
+        }
+      }
       ConvParams p{};
       p.in = make_view(c, s.in); p.out = make_view(c, s.out);
       if (s.res.t >= 0) p.res = make_view(c, s.res);
@@ -524,7 +549,7 @@ int run_network(emd_engine* e, const float* d_in, float* d_out, int n, int mode,
   e->last_n = n; e->last_et = c.et;
   for (size_t i = 0; i < e->steps.size(); ++i) {
     if (e->profile) CU(e, cudaEventRecord(e->events[i], s));
-    cudaError_t r = run_step(c, e->steps[i]);
+    cudaError_t r = run_step(c, (int)i);
     if (r != cudaSuccess) return fail(e, EMD_ECUDA, "step %s: %s", e->steps[i].name.c_str(), cudaGetErrorString(r));
   }
   if (e->profile) {
@@ -939,7 +964,7 @@ int emd_run_layer(emd_engine* e, const char* name, const float* in, const float*
   c.ov.push_back(Override{rout.t, d_out});
   if (rres.t >= 0) c.ov.push_back(Override{rres.t, d_res});
   for (int i : idx) {
-    cudaError_t r = run_step(c, e->steps[i]);
+    cudaError_t r = run_step(c, i);
     if (r != cudaSuccess) return fail(e, EMD_ECUDA, "step %s: %s", e->steps[i].name.c_str(), cudaGetErrorString(r));
   }
   View v; v.ptr = d_out; v.H = to.H; v.W = to.W; v.pitch = rout.C; v.coff = 0; v.C = rout.C;

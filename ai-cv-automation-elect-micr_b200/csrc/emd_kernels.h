@@ -60,6 +60,18 @@ struct ResizeParams {        // TF1 legacy bilinear (DMG:344, 494) + optional af
   int relu6;
 };
 
+// 1-channel input layers (network stem): out[p][c] = relu6(scale[c] * (w[c] * d(p)) + shift[c]) with
+// d(p) = depthwise 3x3 of the input at p (cnn0, DMG:396) or the input sampled at stride `istride`
+// (residual0, DMG:407).  Input is always the FP32 network input.
+struct StemParams {
+  const float* in; int IH, IW;
+  View out; int N;
+  const float* dw;           // [9] or nullptr
+  const float* w;            // [Cout]
+  const float* scale; const float* shift;
+  int istride, relu6;
+};
+
 struct PoolParams { View in, out; int N; };   // 2x2 average, stride 2 (DMG:331-335)
 
 // launchers (emd_kernels_simt.cu); et = element type of the activations
@@ -67,12 +79,15 @@ cudaError_t launch_conv_simt(const ConvParams& p, int et, cudaStream_t s);
 cudaError_t launch_dw3x3(const DwParams& p, int et, cudaStream_t s);
 cudaError_t launch_resize(const ResizeParams& p, int et, cudaStream_t s);
 cudaError_t launch_avgpool(const PoolParams& p, int et, cudaStream_t s);
+cudaError_t launch_stem(const StemParams& p, int et, cudaStream_t s);
 cudaError_t launch_cast(const float* src, void* dst, size_t n, int et, cudaStream_t s);
 cudaError_t launch_uncast(const void* src, float* dst, size_t n, int et, cudaStream_t s);
 
 // emd_dw.cu: TMA-fed depthwise 3x3 (stride 1) for the 16-bit modes
 bool dw_tma_supported(const DwParams& p, int et);
 cudaError_t launch_dw_tma(const DwParams& p, int et, int num_sms, cudaStream_t s);
+bool final_tma_supported(const ConvParams& p, int et);
+cudaError_t launch_final_tma(const ConvParams& p, float scale, float shift, int et, int num_sms, cudaStream_t s);
 
 // emd_umma.cu: tcgen05 implicit GEMM (16-bit element types only)
 bool umma_supported(const ConvParams& p, int et);
