@@ -438,12 +438,58 @@ cudaError_t run_conv(ExecCtx& c, ConvParams& p, const Step& s) {
     p.w = s.wr[c.et];
     return launch_final_tma(p, s.scale0, s.shift0, c.et, e->num_sms, c.s);
   }
+  if (c.et != ET_F32 && e->use_umma && s.w16[c.et] && fused_supported(p, c.et, nullptr)) {
+    e->umma_launches++;
+    return launch_conv_fused(p, c.et, nullptr, e->num_sms, c.s);
+  }
   if (c.et != ET_F32 && e->use_umma && s.w16[c.et] && umma_supported(p, c.et)) {
     e->umma_launches++;
     return launch_conv_umma(p, c.et, e->num_sms, c.s);
   }
   if (c.et != ET_F32 && s.wr[c.et]) p.w = s.wr[c.et];
   return launch_conv_simt(p, c.et, c.s);
+}
+
+// ConvParams of a plain (non-stem) SK_CONV step
+void conv_params(const ExecCtx& c, const Step& s, ConvParams& p) {
+  emd_engine* e = c.e;
+  const Tensor& ti = e->tensors[s.in.t];
+  const Tensor& to = e->tensors[s.out.t];
+  p.in = make_view(c, s.in); p.out = make_view(c, s.out);
+  if (s.res.t >= 0) p.res = make_view(c, s.res);
+  p.N = c.n; p.MH = to.H; p.MW = to.W;
+  p.istride = s.stride; p.ostride = 1; p.oy0 = p.ox0 = 0;
+  p.Cin = s.Cin; p.Cout = s.Cout; p.w = s.w; p.w16 = s.w16[c.et]; p.scale = s.scale; p.shift = s.shift;
+  p.relu6 = s.relu6; p.clip01 = s.clip01; p.out_f32 = to.external; p.in_f32 = ti.external;
+  p.wtaps = s.k * s.k;
+  // taps: TF SAME. stride 1: symmetric (k/2)*rate.  stride 2 only occurs with k = 1 here (DMG:365-370).
+  const int half = s.k / 2;
+  p.ntaps = 0;
+  for (int ky = 0; ky < s.k; ++ky)
+    for (int kx = 0; kx < s.k; ++kx) {
+      const int dy = (ky - half) * s.rate, dx = (kx - half) * s.rate;
+      if (std::abs(dy) >= ti.H || std::abs(dx) >= ti.W) continue;  // tap never in bounds (dilation >= map)
+      p.dy[p.ntaps] = dy; p.dx[p.ntaps] = dx; p.wrow[p.ntaps] = ky * s.k + kx; p.ntaps++;
+    }
+}
+
+// A stride-1 separable block whose pointwise GEMM can take the depthwise 3x3 as its A-operand producer
+// (emd_fused.cu, dw mode): the SK_DW step is skipped and the SK_CONV step launches the fused kernel.
+bool dw_fusable(const ExecCtx& c, int conv_idx, ConvParams* out) {
+  emd_engine* e = c.e;
+  if (c.et == ET_F32 || !e->use_umma || conv_idx < 1 || conv_idx >= (int)e->steps.size()) return false;
+  const Step& s = e->steps[conv_idx];
+  const Step& d = e->steps[conv_idx - 1];
+  if (s.kind != SK_CONV || s.k != 1 || s.stride != 1 || !s.w16[c.et]) return false;
+  if (d.kind != SK_DW || d.layer != s.layer || d.stride != 1 || d.rate != 1 || d.Cin == 1) return false;
+  if (e->tensors[d.in.t].external) return false;
+  ConvParams p{};
+  conv_params(c, s, p);
+  p.in = make_view(c, d.in);
+  p.in_f32 = 0;
+  if (!fused_supported(p, c.et, d.dw)) return false;
+  if (out) *out = p;
+  return true;
 }
 
 cudaError_t run_step(ExecCtx& c, int idx) {
@@ -454,6 +500,7 @@ cudaError_t run_step(ExecCtx& c, int idx) {
   switch (s.kind) {
     case SK_DW: {
       if (s.Cin == 1) return cudaSuccess;  // 1-channel stem: the depthwise is fused into the pointwise kernel below
+      if (dw_fusable(c, idx + 1, nullptr)) return cudaSuccess;  // computed inside the pointwise GEMM's producer warps
       DwParams p{};
       p.in = make_view(c, s.in); p.out = make_view(c, s.out);
       p.N = c.n; p.OH = to.H; p.OW = to.W; p.stride = s.stride; p.rate = s.rate;
@@ -492,22 +539,13 @@ cudaError_t run_step(ExecCtx& c, int idx) {
         }
       }
       ConvParams p{};
-      p.in = make_view(c, s.in); p.out = make_view(c, s.out);
-      if (s.res.t >= 0) p.res = make_view(c, s.res);
-      p.N = c.n; p.MH = to.H; p.MW = to.W;
-      p.istride = s.stride; p.ostride = 1; p.oy0 = p.ox0 = 0;
-      p.Cin = s.Cin; p.Cout = s.Cout; p.w = s.w; p.w16 = s.w16[c.et]; p.scale = s.scale; p.shift = s.shift;
-      p.relu6 = s.relu6; p.clip01 = s.clip01; p.out_f32 = to.external; p.in_f32 = ti.external;
-      p.wtaps = s.k * s.k;
-      // taps: TF SAME. stride 1: symmetric (k/2)*rate.  stride 2 only occurs with k = 1 here (DMG:365-370).
-      const int half = s.k / 2;
-      p.ntaps = 0;
-      for (int ky = 0; ky < s.k; ++ky)
-        for (int kx = 0; kx < s.k; ++kx) {
-          const int dy = (ky - half) * s.rate, dx = (kx - half) * s.rate;
-          if (std::abs(dy) >= ti.H || std::abs(dx) >= ti.W) continue;  // tap never in bounds (dilation >= map)
-          p.dy[p.ntaps] = dy; p.dx[p.ntaps] = dx; p.wrow[p.ntaps] = ky * s.k + kx; p.ntaps++;
-        }
+      if (dw_fusable(c, idx, &p)) {
+        e->launches++;
+        e->umma_launches++;
+        return launch_conv_fused(p, c.et, e->steps[idx - 1].dw, e->num_sms, c.s);
+      }
+      p = ConvParams{};
+      conv_params(c, s, p);
       return run_conv(c, p, s);
     }
     case SK_DECONV: {
@@ -606,6 +644,8 @@ int emd_create(emd_engine** out, int device, int cropsize, int variant, int max_
   e->use_umma = !(env && env[0] == '1');
   env = getenv("EMD_DISABLE_TMA");
   umma_set_tma(!(env && env[0] == '1'));
+  env = getenv("EMD_DISABLE_FUSED");
+  fused_set_enabled(!(env && env[0] == '1'));
 #define CUC(call)                                                                                       \
   do {                                                                                                  \
     cudaError_t _r = (call);                                                                            \

@@ -89,12 +89,40 @@ cudaError_t launch_dw_tma(const DwParams& p, int et, int num_sms, cudaStream_t s
 bool final_tma_supported(const ConvParams& p, int et);
 cudaError_t launch_final_tma(const ConvParams& p, float scale, float shift, int et, int num_sms, cudaStream_t s);
 
+// Split of the output channels into UMMA N tiles (<= 256 columns each, multiples of 16); the packed
+// B operand (umma_pack_weights) and both tcgen05 kernels share it.
+constexpr int kMaxNTiles = 4;
+struct NTiling { int nt; int n0[kMaxNTiles]; int rows[kMaxNTiles]; int rows_before[kMaxNTiles]; int maxrows; };
+inline NTiling make_ntiling(int Cout) {
+  NTiling t;
+  const int cpad = (Cout + 15) & ~15;
+  t.nt = (cpad + 255) / 256;
+  const int base = (((cpad + t.nt - 1) / t.nt) + 15) & ~15;
+  t.maxrows = 0;
+  int acc = 0;
+  for (int i = 0; i < kMaxNTiles; ++i) { t.n0[i] = 0; t.rows[i] = 0; t.rows_before[i] = 0; }
+  for (int i = 0; i < t.nt && i < kMaxNTiles; ++i) {
+    t.n0[i] = i * base;
+    t.rows[i] = (cpad - i * base) < base ? (cpad - i * base) : base;
+    t.rows_before[i] = acc;
+    acc += t.rows[i];
+    if (t.rows[i] > t.maxrows) t.maxrows = t.rows[i];
+  }
+  return t;
+}
+
 // emd_umma.cu: tcgen05 implicit GEMM (16-bit element types only)
 bool umma_supported(const ConvParams& p, int et);
 cudaError_t launch_conv_umma(const ConvParams& p, int et, int num_sms, cudaStream_t s);
 // packs FP32 [K][Cout] weights into the UMMA tile image; returns bytes needed when dst == nullptr
 void umma_set_tma(bool on);   // A tiles through TMA tensor maps (default) or the cp.async gather only
 size_t umma_pack_weights(const float* w, int ntaps, int Cin, int Cout, int et, void* dst_host);
+
+// emd_fused.cu: second-generation tcgen05 kernel for block-tiled output grids (TMA-store epilogue; optional
+// depthwise-3x3 producer: dw = [9][Cin] FP32 weights, p.in = the depthwise input)
+bool fused_supported(const ConvParams& p, int et, const float* dw);
+cudaError_t launch_conv_fused(const ConvParams& p, int et, const float* dw, int num_sms, cudaStream_t s);
+void fused_set_enabled(bool on);
 
 // emd_kernels_wrap.cu: whole-image wrapper kernels
 cudaError_t launch_minmax(const void* img, int in_f64, size_t n, double* d_minmax /*[2]*/, void* d_partial,

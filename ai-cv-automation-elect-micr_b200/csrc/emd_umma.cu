@@ -34,29 +34,8 @@ constexpr int kBK = 64;             // channels per K block (128 bytes = one swi
 constexpr int kAStageBytes = kBM * kBK * 2;
 constexpr int kThreads = 320;
 constexpr int kLag = 3;             // A-loader look-ahead in stages
-constexpr int kMaxNTiles = 4;
 constexpr int kMaxCout = 1024;
 constexpr int kSmemLimit = 227 * 1024;
-
-struct NTiling { int nt; int n0[kMaxNTiles]; int rows[kMaxNTiles]; int rows_before[kMaxNTiles]; int maxrows; };
-
-inline NTiling make_ntiling(int Cout) {
-  NTiling t;
-  const int cpad = (Cout + 15) & ~15;
-  t.nt = (cpad + 255) / 256;
-  const int base = (((cpad + t.nt - 1) / t.nt) + 15) & ~15;
-  t.maxrows = 0;
-  int acc = 0;
-  for (int i = 0; i < kMaxNTiles; ++i) { t.n0[i] = 0; t.rows[i] = 0; t.rows_before[i] = 0; }
-  for (int i = 0; i < t.nt; ++i) {
-    t.n0[i] = i * base;
-    t.rows[i] = (cpad - i * base) < base ? (cpad - i * base) : base;
-    t.rows_before[i] = acc;
-    acc += t.rows[i];
-    if (t.rows[i] > t.maxrows) t.maxrows = t.rows[i];
-  }
-  return t;
-}
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
