@@ -38,8 +38,24 @@ constexpr int kMaxC = 768;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kEpiThreads = 128;
 constexpr int kBaseThreads = 192;                           // epilogue + MMA + producer
-constexpr int kMathThreads = 256;
+constexpr int kMathThreads = 512;                           // two groups of 8 warps, alternating chunks
+constexpr int kGroupWarps = 8;
 constexpr int kMaxStages = 8;
+
+// unsigned division by a runtime constant (Granlund-Montgomery): q = (t + ((x - t) >> 1)) >> (l - 1), t = mulhi(m, x)
+struct FastDiv { uint32_t d, m, l; };
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d; f.l = 0;
+  while ((1ull << f.l) < d) ++f.l;
+  f.m = (uint32_t)((((1ull << f.l) - d) << 32) / d + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv& f) {
+  if (f.d == 1) return x;
+  const uint32_t t = __umulhi(f.m, x);
+  return (t + ((x - t) >> 1)) >> (f.l - 1);
+}
 
 struct FusedArgs {
   ConvParams p;
@@ -49,6 +65,7 @@ struct FusedArgs {
   int b_stage_bytes, nchunks, w_kblocks, m_tiles, tiles_x, tiles_per_img;
   int tmem_cols, acc_stride;
   int has_res;
+  FastDiv d_nt, d_tpi, d_tx, d_chunks;   // by nt.nt, tiles_per_img, tiles_x, nchunks
   const float* dw_w;         // [9][Cin] FP32, tap-major (dw mode)
 };
 
@@ -85,14 +102,63 @@ template <> struct Cv<__half> {
 };
 
 __device__ __forceinline__ void tile_coords(const FusedArgs& a, int mt, int& n_img, int& y0, int& x0) {
-  n_img = mt / a.tiles_per_img;
+  n_img = (int)fdiv((uint32_t)mt, a.d_tpi);
   const int rem = mt - n_img * a.tiles_per_img;
-  const int by = rem / a.tiles_x;
+  const int by = (int)fdiv((uint32_t)rem, a.d_tx);
   y0 = by * kTH;
   x0 = (rem - by * a.tiles_x) * kTW;
 }
 
-template <typename T, bool kDw>
+// position in a ring of n pipeline stages plus the mbarrier phase parity of the current pass
+struct Ring {
+  int idx, n;
+  uint32_t phase;
+  __device__ __forceinline__ Ring(int start, int n_) : idx(start % n_), n(n_), phase((uint32_t)((start / n_) & 1)) {}
+  __device__ __forceinline__ void advance(int by) {   // by <= n
+    idx += by;
+    if (idx >= n) { idx -= n; phase ^= 1u; }
+  }
+};
+
+// one 32-column half of an output slab: registers v (FP32 accumulators of this thread's pixel row) -> scale/shift ->
+// ReLU6 -> (+ residual already sitting in the slab) -> 16-bit -> swizzled slab row
+template <typename T, bool kRes, bool kRelu6>
+__device__ __forceinline__ void epi_half(const uint32_t (&v)[32], const float* __restrict__ sc, const float* __restrict__ sh,
+                                         uint8_t* srow, int h, int rsw) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {         // 16-byte chunk = 8 channels
+    const float4 sc0 = *reinterpret_cast<const float4*>(sc + 8 * k), sc1 = *reinterpret_cast<const float4*>(sc + 8 * k + 4);
+    const float4 sh0 = *reinterpret_cast<const float4*>(sh + 8 * k), sh1 = *reinterpret_cast<const float4*>(sh + 8 * k + 4);
+    float2 y[4];
+    y[0] = ffma2(make_float2(__uint_as_float(v[8 * k + 0]), __uint_as_float(v[8 * k + 1])), make_float2(sc0.x, sc0.y), make_float2(sh0.x, sh0.y));
+    y[1] = ffma2(make_float2(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3])), make_float2(sc0.z, sc0.w), make_float2(sh0.z, sh0.w));
+    y[2] = ffma2(make_float2(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5])), make_float2(sc1.x, sc1.y), make_float2(sh1.x, sh1.y));
+    y[3] = ffma2(make_float2(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7])), make_float2(sc1.z, sc1.w), make_float2(sh1.z, sh1.w));
+    uint4* slot = reinterpret_cast<uint4*>(srow + ((((h * 4 + k) ^ rsw)) << 4));
+    uint4 o;
+    if (kRes) {
+      const uint4 r = *slot;
+      const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float lo = y[e].x, hi = y[e].y;
+        if (kRelu6) { lo = fminf(fmaxf(lo, 0.f), 6.f); hi = fminf(fmaxf(hi, 0.f), 6.f); }
+        const float2 rr = Cv<T>::up(rw[e]);
+        ow[e] = Cv<T>::pack(lo + rr.x, hi + rr.y);
+      }
+      o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    } else if (kRelu6) {
+      o = make_uint4(Cv<T>::pack_relu6(y[0].x, y[0].y), Cv<T>::pack_relu6(y[1].x, y[1].y), Cv<T>::pack_relu6(y[2].x, y[2].y),
+                     Cv<T>::pack_relu6(y[3].x, y[3].y));
+    } else {
+      o = make_uint4(Cv<T>::pack(y[0].x, y[0].y), Cv<T>::pack(y[1].x, y[1].y), Cv<T>::pack(y[2].x, y[2].y), Cv<T>::pack(y[3].x, y[3].y));
+    }
+    *slot = o;
+  }
+}
+
+template <typename T, bool kDw, bool kRes>
 __global__ void __launch_bounds__(kDw ? kBaseThreads + kMathThreads : kBaseThreads, 1)
 fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ CUtensorMap tmap_in,
                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res) {
@@ -128,19 +194,19 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
-      mbar_init(bar_afull + 8u * s, kDw ? kMathThreads / 32 : 1);   // dw: one arrive per math warp; taps: expect_tx arrive
+      mbar_init(bar_afull + 8u * s, kDw ? kGroupWarps : 1);   // dw: one arrive per math warp of the group; taps: expect_tx arrive
       mbar_init(bar_aempty + 8u * s, 1);
       mbar_init(bar_bfull + 8u * s, 1);
       mbar_init(bar_bempty + 8u * s, 1);
       mbar_init(bar_hfull + 8u * s, 1);
-      mbar_init(bar_hempty + 8u * s, kMathThreads / 32);
+      mbar_init(bar_hempty + 8u * s, kGroupWarps);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, kEpiThreads); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, kEpiThreads / 32); }
     for (int i = 0; i < kMaxRing; ++i) mbar_init(bar_rfull + 8u * i, 1);
     fence_barrier_init();
     prefetch_tmap(&tmap_in);
     prefetch_tmap(&tmap_out);
-    if (a.has_res) prefetch_tmap(&tmap_res);
+    if (kRes) prefetch_tmap(&tmap_res);
   }
   if (warp == 4) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
   tc_fence_before();
@@ -152,42 +218,51 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
     // ===================== TMA producer =====================
     if (lane == 0) {
       const char* wbase = reinterpret_cast<const char*>(p.w16);
-      int it = 0;
+      Ring ra(0, SA), rb(0, SB), rh(0, kDw ? SH : 1);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / a.nt.nt, ntile = tile - mt * a.nt.nt;
+        const int mt = (int)fdiv((uint32_t)tile, a.d_nt), ntile = tile - mt * a.nt.nt;
         const uint32_t bytes = (uint32_t)a.nt.rows[ntile] * 128u;
         // packed weights: [n_tile][weight k-block = tap*nchunks + chunk][rows x 128 B, swizzled]
         const char* tbase = wbase + (size_t)a.nt.rows_before[ntile] * a.w_kblocks * 128;
         int n_img, y0, x0;
         tile_coords(a, mt, n_img, y0, x0);
         if (kDw) {
-          for (int c = 0; c < a.nchunks; ++c, ++it) {
-            const int sh = it % SH, sb = it % SB;
-            mbar_wait(bar_hempty + 8u * sh, (uint32_t)(((it / SH) & 1) ^ 1));
-            mbar_arrive_expect_tx(bar_hfull + 8u * sh, kHaloBytes);
-            tma_load_4d(sH + (uint32_t)sh * kHaloBytes, &tmap_in, c * kBK, x0 - 1, y0 - 1, n_img, bar_hfull + 8u * sh);
-            mbar_wait(bar_bempty + 8u * sb, (uint32_t)(((it / SB) & 1) ^ 1));
-            mbar_arrive_expect_tx(bar_bfull + 8u * sb, bytes);
-            bulk_g2s(sB + (uint32_t)sb * a.b_stage_bytes, tbase + (size_t)(p.wrow[0] * a.nchunks + c) * bytes, bytes, bar_bfull + 8u * sb);
+          const char* wsrc = tbase + (size_t)(p.wrow[0] * a.nchunks) * bytes;
+          for (int c = 0; c < a.nchunks; ++c) {
+            mbar_wait(bar_hempty + 8u * rh.idx, rh.phase ^ 1u);
+            mbar_arrive_expect_tx(bar_hfull + 8u * rh.idx, kHaloBytes);
+            tma_load_4d(sH + (uint32_t)rh.idx * kHaloBytes, &tmap_in, c * kBK, x0 - 1, y0 - 1, n_img, bar_hfull + 8u * rh.idx);
+            mbar_wait(bar_bempty + 8u * rb.idx, rb.phase ^ 1u);
+            mbar_arrive_expect_tx(bar_bfull + 8u * rb.idx, bytes);
+            bulk_g2s(sB + (uint32_t)rb.idx * a.b_stage_bytes, wsrc, bytes, bar_bfull + 8u * rb.idx);
+            wsrc += bytes;
+            rh.advance(1); rb.advance(1);
           }
         } else {
-          for (int kb = 0; kb < kblocks; ++kb, ++it) {
-            const int t = kb / a.nchunks, c = kb - t * a.nchunks;
-            const int s = it % SA;
-            mbar_wait(bar_aempty + 8u * s, (uint32_t)(((it / SA) & 1) ^ 1));
-            const uint32_t bar = bar_afull + 8u * s;
-            mbar_arrive_expect_tx(bar, bytes + (uint32_t)kAStageBytes);
-            tma_load_4d(sA + (uint32_t)s * kAStageBytes, &tmap_in, c * kBK, x0 * p.istride + p.dx[t], y0 * p.istride + p.dy[t], n_img, bar);
-            bulk_g2s(sB + (uint32_t)s * a.b_stage_bytes, tbase + (size_t)(p.wrow[t] * a.nchunks + c) * bytes, bytes, bar);
+          const int xb = x0 * p.istride, yb = y0 * p.istride;
+          for (int t = 0; t < p.ntaps; ++t) {
+            const char* wsrc = tbase + (size_t)(p.wrow[t] * a.nchunks) * bytes;
+            const int xt = xb + p.dx[t], yt = yb + p.dy[t];
+            for (int c = 0; c < a.nchunks; ++c) {
+              mbar_wait(bar_aempty + 8u * ra.idx, ra.phase ^ 1u);
+              const uint32_t bar = bar_afull + 8u * ra.idx;
+              mbar_arrive_expect_tx(bar, bytes + (uint32_t)kAStageBytes);
+              tma_load_4d(sA + (uint32_t)ra.idx * kAStageBytes, &tmap_in, c * kBK, xt, yt, n_img, bar);
+              bulk_g2s(sB + (uint32_t)ra.idx * a.b_stage_bytes, wsrc, bytes, bar);
+              wsrc += bytes;
+              ra.advance(1);
+            }
           }
         }
       }
     }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
-    int it = 0, tcount = 0;
+    Ring ra(0, SA), rb(0, SB);
+    int tcount = 0;
+    const int last_ksteps = (p.Cin - (a.nchunks - 1) * kBK + 15) >> 4;   // K=16 steps of the last (possibly partial) chunk
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const int ntile = tile % a.nt.nt;
+      const int ntile = tile - (int)fdiv((uint32_t)tile, a.d_nt) * a.nt.nt;
       const uint32_t n = (uint32_t)a.nt.rows[ntile];
       // instruction descriptor: D = F32 (bits 4-5), A/B format (bits 7-9 / 10-12), K-major A and B, N>>3 at 17-22, M>>4 at 24-28
       const uint32_t idesc = (1u << 4) | (Cv<T>::kFmt << 7) | (Cv<T>::kFmt << 10) | ((n >> 3) << 17) | ((kBM >> 4) << 24);
@@ -195,15 +270,14 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
       mbar_wait(bar_tempty + 8u * acc, (uint32_t)(((tcount >> 1) & 1) ^ 1));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.acc_stride);
-      for (int kb = 0; kb < kblocks; ++kb, ++it) {
-        const int c = kb % a.nchunks;
-        const int sa = it % SA, sb = kDw ? it % SB : sa;
-        mbar_wait(bar_afull + 8u * sa, (uint32_t)((it / SA) & 1));
-        if (kDw) mbar_wait(bar_bfull + 8u * sb, (uint32_t)((it / SB) & 1));
+      int c = 0;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int sa = ra.idx, sb = kDw ? rb.idx : sa;
+        mbar_wait(bar_afull + 8u * sa, ra.phase);
+        if (kDw) mbar_wait(bar_bfull + 8u * sb, rb.phase);
         tc_fence_after();
         if (lane == 0) {
-          const int kvalid = min(kBK, p.Cin - c * kBK);
-          const int ksteps = (kvalid + 15) >> 4;
+          const int ksteps = (c == a.nchunks - 1) ? last_ksteps : 4;
           const uint64_t adesc = make_sdesc(sA + (uint32_t)sa * kAStageBytes);
           const uint64_t bdesc = make_sdesc(sB + (uint32_t)sb * a.b_stage_bytes);
           for (int ks = 0; ks < ksteps; ++ks)  // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
@@ -213,6 +287,9 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
           if (kb == kblocks - 1) umma_commit(bar_tfull + 8u * acc);  // accumulator complete
         }
         __syncwarp();
+        ra.advance(1);
+        if (kDw) rb.advance(1);
+        if (++c == a.nchunks) c = 0;
       }
     }
   } else if (warp < 4) {
@@ -221,23 +298,24 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
     const uint32_t row_off = (uint32_t)tid * 128u;
     const int rsw = tid & 7;
     // residual prefetch cursor (thread 0): slab sequence number -> (tile, slab)
-    int pf_tile = blockIdx.x, pf_slab = 0, pf_q = 0;
+    int pf_tile = blockIdx.x, pf_slab = 0, pf_buf = 0;
     auto prefetch_res = [&]() {
-      if (pf_tile >= total_tiles) return;
-      const int mt = pf_tile / a.nt.nt, ntile = pf_tile - mt * a.nt.nt;
-      int n_img, y0, x0;
-      tile_coords(a, mt, n_img, y0, x0);
-      const int buf = pf_q % R;
-      mbar_arrive_expect_tx(bar_rfull + 8u * buf, kSlabBytes);
-      tma_load_4d(sO + (uint32_t)buf * kSlabBytes, &tmap_res, a.nt.n0[ntile] + pf_slab * 64, x0, y0, n_img, bar_rfull + 8u * buf);
-      ++pf_q;
-      if (++pf_slab * 64 >= a.nt.rows[ntile]) { pf_slab = 0; pf_tile += gridDim.x; }
+      if (pf_tile < total_tiles) {
+        const int mt = (int)fdiv((uint32_t)pf_tile, a.d_nt), ntile = pf_tile - mt * a.nt.nt;
+        int n_img, y0, x0;
+        tile_coords(a, mt, n_img, y0, x0);
+        mbar_arrive_expect_tx(bar_rfull + 8u * pf_buf, kSlabBytes);
+        tma_load_4d(sO + (uint32_t)pf_buf * kSlabBytes, &tmap_res, a.nt.n0[ntile] + pf_slab * 64, x0, y0, n_img, bar_rfull + 8u * pf_buf);
+        if (++pf_slab * 64 >= a.nt.rows[ntile]) { pf_slab = 0; pf_tile += gridDim.x; }
+      }
+      if (++pf_buf == R) pf_buf = 0;
     };
-    if (a.has_res && tid == 0)
+    if (kRes && tid == 0)
       for (int i = 0; i < R - 1; ++i) prefetch_res();
-    int tcount = 0, q = 0;
+    int tcount = 0;
+    Ring rq(0, R);                           // output staging slab
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const int mt = tile / a.nt.nt, ntile = tile - mt * a.nt.nt;
+      const int mt = (int)fdiv((uint32_t)tile, a.d_nt), ntile = tile - mt * a.nt.nt;
       const int n0 = a.nt.n0[ntile], n = a.nt.rows[ntile];
       int n_img, y0, x0;
       tile_coords(a, mt, n_img, y0, x0);
@@ -246,10 +324,10 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * a.acc_stride);
       const int nslabs = (n + 63) >> 6;
-      for (int j = 0; j < nslabs; ++j, ++q) {
-        const int buf = q % R;
+      for (int j = 0; j < nslabs; ++j) {
+        const int buf = rq.idx;
         uint8_t* srow = g_stage + (size_t)buf * kSlabBytes + row_off;
-        if (a.has_res) mbar_wait(bar_rfull + 8u * buf, (uint32_t)((q / R) & 1));
+        if (kRes) mbar_wait(bar_rfull + 8u * buf, rq.phase);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c0 = j * 64 + h * 32;        // column within the N tile
@@ -259,42 +337,11 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
             tmem_ld_wait();
             if (j == nslabs - 1 && (h == 1 || c0 + 32 >= n)) {  // last read of this accumulator: hand it back to the MMA warp
               tc_fence_before();
-              mbar_arrive(bar_tempty + 8u * acc);
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_tempty + 8u * acc);
             }
-            const float* sc = s_scale + n0 + c0;
-            const float* sh = s_shift + n0 + c0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {         // 16-byte chunk = 8 channels
-              const float4 sc0 = *reinterpret_cast<const float4*>(sc + 8 * k), sc1 = *reinterpret_cast<const float4*>(sc + 8 * k + 4);
-              const float4 sh0 = *reinterpret_cast<const float4*>(sh + 8 * k), sh1 = *reinterpret_cast<const float4*>(sh + 8 * k + 4);
-              float2 y[4];
-              y[0] = ffma2(make_float2(__uint_as_float(v[8 * k + 0]), __uint_as_float(v[8 * k + 1])), make_float2(sc0.x, sc0.y), make_float2(sh0.x, sh0.y));
-              y[1] = ffma2(make_float2(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3])), make_float2(sc0.z, sc0.w), make_float2(sh0.z, sh0.w));
-              y[2] = ffma2(make_float2(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5])), make_float2(sc1.x, sc1.y), make_float2(sh1.x, sh1.y));
-              y[3] = ffma2(make_float2(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7])), make_float2(sc1.z, sc1.w), make_float2(sh1.z, sh1.w));
-              uint4* slot = reinterpret_cast<uint4*>(srow + ((((h * 4 + k) ^ rsw)) << 4));
-              uint4 o;
-              if (a.has_res) {
-                const uint4 r = *slot;
-                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-                uint32_t ow[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float lo = y[e].x, hi = y[e].y;
-                  if (p.relu6) { lo = fminf(fmaxf(lo, 0.f), 6.f); hi = fminf(fmaxf(hi, 0.f), 6.f); }
-                  const float2 rr = Cv<T>::up(rw[e]);
-                  ow[e] = Cv<T>::pack(lo + rr.x, hi + rr.y);
-                }
-                o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-              } else if (p.relu6) {
-                o = make_uint4(Cv<T>::pack_relu6(y[0].x, y[0].y), Cv<T>::pack_relu6(y[1].x, y[1].y), Cv<T>::pack_relu6(y[2].x, y[2].y),
-                               Cv<T>::pack_relu6(y[3].x, y[3].y));
-              } else {
-                o = make_uint4(Cv<T>::pack(y[0].x, y[0].y), Cv<T>::pack(y[1].x, y[1].y), Cv<T>::pack(y[2].x, y[2].y),
-                               Cv<T>::pack(y[3].x, y[3].y));
-              }
-              *slot = o;
-            }
+            if (p.relu6) epi_half<T, kRes, true>(v, s_scale + n0 + c0, s_shift + n0 + c0, srow, h, rsw);
+            else epi_half<T, kRes, false>(v, s_scale + n0 + c0, s_shift + n0 + c0, srow, h, rsw);
           }
         }
         fence_proxy_async();               // make this thread's slab writes visible to the TMA engine
@@ -305,77 +352,76 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
         if (tid == 0) {
           tma_store_4d(&tmap_out, sO + (uint32_t)buf * kSlabBytes, n0 + j * 64, x0, y0, n_img);
           bulk_commit();
-          if (a.has_res) {                 // refill the slab stored one iteration ago with the residual of slab q + R - 1
+          if (kRes) {                      // refill the slab stored one iteration ago with the residual of the slab R-1 ahead
             bulk_wait_read<1>();
             prefetch_res();
           }
         }
+        rq.advance(1);
       }
     }
     if (tid == 0) bulk_wait<0>();
   } else if (kDw) {
     // ===================== depthwise math warps: halo -> 3x3 window in registers -> swizzled A stage =====================
-    const int tm = threadIdx.x - kBaseThreads;           // 0..255
-    const int qc = tm & 7, col = (tm >> 3) & 15, half = tm >> 7;
-    const uint32_t a_thread = (uint32_t)((4 * half) * kTW + col) * 128u + (uint32_t)((qc ^ (col & 7)) << 4);
-    float2 w[9][4];
+    // Two groups of 8 warps take alternate (tile, chunk) items.  Thread = 4 channels x 1 pixel column x 8 rows:
+    // 16 lanes read one 128-byte halo pixel per LDS.64, the window slides down the column in registers.
+    const int tm = threadIdx.x - kBaseThreads;           // 0..511
+    const int grp = tm >> 8, tg = tm & 255;
+    const int cq = tg & 15, col = tg >> 4;
+    const uint32_t a_thread = (uint32_t)col * 128u + (uint32_t)((((cq >> 1) ^ (col & 7)) << 4) + (cq & 1) * 8);
+    const uint32_t h_thread = (uint32_t)col * (kBK * 2) + (uint32_t)cq * 8;
+    float2 w[9][2];
     int cur_c = -1;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      for (int c = 0; c < a.nchunks; ++c, ++it) {
-        const int ch = c * kBK + qc * 8;
-        if (c != cur_c) {
-          cur_c = c;
-          const bool ch_ok = ch < p.Cin;
+    const int items = ((total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * a.nchunks;   // this CTA's (tile, chunk) items
+    Ring rh(grp, SH), ra(grp, SA);
+    int c = grp % a.nchunks;
+    for (int it = grp; it < items; it += 2) {
+      if (c != cur_c) {
+        cur_c = c;
+        const int ch = c * kBK + cq * 4;
+        const bool ch_ok = ch < p.Cin;
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
-            if (ch_ok) {
-              w0 = __ldg(reinterpret_cast<const float4*>(a.dw_w + t * p.Cin + ch));
-              w1 = __ldg(reinterpret_cast<const float4*>(a.dw_w + t * p.Cin + ch + 4));
-            }
-            w[t][0] = make_float2(w0.x, w0.y); w[t][1] = make_float2(w0.z, w0.w);
-            w[t][2] = make_float2(w1.x, w1.y); w[t][3] = make_float2(w1.z, w1.w);
-          }
-        }
-        const int sh = it % SH, sa = it % SA;
-        mbar_wait(bar_hfull + 8u * sh, (uint32_t)((it / SH) & 1));
-        mbar_wait(bar_aempty + 8u * sa, (uint32_t)(((it / SA) & 1) ^ 1));
-        const uint8_t* hb = g_halo + (size_t)sh * kHaloBytes + qc * 16;
-        uint8_t* ab = smem + (size_t)sa * kAStageBytes + a_thread;
-        float2 win[3][3][4];
-        auto load_row = [&](int hy, float2 (&dst)[3][4]) {
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const uint4 u = *reinterpret_cast<const uint4*>(hb + (size_t)(hy * kHaloW + col + kx) * (kBK * 2));
-            dst[kx][0] = Cv<T>::up(u.x); dst[kx][1] = Cv<T>::up(u.y); dst[kx][2] = Cv<T>::up(u.z); dst[kx][3] = Cv<T>::up(u.w);
-          }
-        };
-        load_row(4 * half + 0, win[0]);
-        load_row(4 * half + 1, win[1]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          load_row(4 * half + i + 2, win[(i + 2) % 3]);
-          float2 acc[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[j] = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-              for (int j = 0; j < 4; ++j) acc[j] = ffma2(win[(i + ky) % 3][kx][j], w[ky * 3 + kx][j], acc[j]);
-          const uint4 o = make_uint4(Cv<T>::pack(acc[0].x, acc[0].y), Cv<T>::pack(acc[1].x, acc[1].y), Cv<T>::pack(acc[2].x, acc[2].y),
-                                     Cv<T>::pack(acc[3].x, acc[3].y));
-          *reinterpret_cast<uint4*>(ab + (size_t)i * kTW * 128) = o;
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(bar_afull + 8u * sa);
-          mbar_arrive(bar_hempty + 8u * sh);
+        for (int t = 0; t < 9; ++t) {
+          float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ch_ok) w0 = __ldg(reinterpret_cast<const float4*>(a.dw_w + t * p.Cin + ch));
+          w[t][0] = make_float2(w0.x, w0.y); w[t][1] = make_float2(w0.z, w0.w);
         }
       }
+      mbar_wait(bar_hfull + 8u * rh.idx, rh.phase);
+      mbar_wait(bar_aempty + 8u * ra.idx, ra.phase ^ 1u);
+      const uint8_t* hb = g_halo + (size_t)rh.idx * kHaloBytes + h_thread;
+      uint8_t* ab = smem + (size_t)ra.idx * kAStageBytes + a_thread;
+      float2 win[3][3][2];
+      auto load_row = [&](int hy, float2 (&dst)[3][2]) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const uint2 u = *reinterpret_cast<const uint2*>(hb + (hy * kHaloW + kx) * (kBK * 2));
+          dst[kx][0] = Cv<T>::up(u.x); dst[kx][1] = Cv<T>::up(u.y);
+        }
+      };
+      load_row(0, win[0]);
+      load_row(1, win[1]);
+#pragma unroll
+      for (int i = 0; i < kTH; ++i) {
+        load_row(i + 2, win[(i + 2) % 3]);
+        float2 acc0 = fmul2(win[i % 3][0][0], w[0][0]), acc1 = fmul2(win[i % 3][0][1], w[0][1]);
+#pragma unroll
+        for (int t = 1; t < 9; ++t) {
+          acc0 = ffma2(win[(i + t / 3) % 3][t % 3][0], w[t][0], acc0);
+          acc1 = ffma2(win[(i + t / 3) % 3][t % 3][1], w[t][1], acc1);
+        }
+        *reinterpret_cast<uint2*>(ab + i * kTW * 128) = make_uint2(Cv<T>::pack(acc0.x, acc0.y), Cv<T>::pack(acc1.x, acc1.y));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_afull + 8u * ra.idx);
+        mbar_arrive(bar_hempty + 8u * rh.idx);
+      }
+      rh.advance(2); ra.advance(2);
+      c += 2;
+      if (c >= a.nchunks) c -= a.nchunks;
+      if (c >= a.nchunks) c -= a.nchunks;
     }
   }
 
@@ -393,18 +439,18 @@ size_t fused_smem_bytes(const FusedArgs& a) {
          (size_t)a.SH * kHaloBytes + 2 * kMaxC * sizeof(float) + (6 * kMaxStages + 4 + kMaxRing) * 8 + 16;
 }
 
-template <typename T, bool kDw>
+template <typename T, bool kDw, bool kRes>
 cudaError_t launch_t(const FusedArgs& a, const CUtensorMap& tin, const CUtensorMap& tout, const CUtensorMap& tres, int grid,
                      size_t smem, cudaStream_t s) {
   static thread_local int attr_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (attr_dev != dev) {
-    cudaError_t r = cudaFuncSetAttribute(fused_conv_kernel<T, kDw>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaError_t r = cudaFuncSetAttribute(fused_conv_kernel<T, kDw, kRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (r != cudaSuccess) return r;
     attr_dev = dev;
   }
-  fused_conv_kernel<T, kDw><<<grid, kDw ? kBaseThreads + kMathThreads : kBaseThreads, smem, s>>>(a, tin, tout, tres);
+  fused_conv_kernel<T, kDw, kRes><<<grid, kDw ? kBaseThreads + kMathThreads : kBaseThreads, smem, s>>>(a, tin, tout, tres);
   return cudaGetLastError();
 }
 
@@ -450,6 +496,8 @@ cudaError_t launch_conv_fused(const ConvParams& p, int et, const float* dw, int 
   a.tiles_per_img = (p.MH / kTH) * a.tiles_x;
   a.m_tiles = p.N * a.tiles_per_img;
   a.b_stage_bytes = ((a.nt.maxrows * 128) + 1023) & ~1023;
+  a.d_nt = make_fastdiv((uint32_t)a.nt.nt); a.d_tpi = make_fastdiv((uint32_t)a.tiles_per_img);
+  a.d_tx = make_fastdiv((uint32_t)a.tiles_x); a.d_chunks = make_fastdiv((uint32_t)a.nchunks);
   int accs = 32;
   while (accs < a.nt.maxrows) accs <<= 1;
   a.acc_stride = accs;
@@ -503,10 +551,14 @@ cudaError_t launch_conv_fused(const ConvParams& p, int et, const float* dw, int 
   const size_t smem = fused_smem_bytes(a);
   const int total_tiles = a.m_tiles * a.nt.nt;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-  if (bf16)
-    return a.dw_mode ? launch_t<__nv_bfloat16, true>(a, tin, tout, tres, grid, smem, s)
-                     : launch_t<__nv_bfloat16, false>(a, tin, tout, tres, grid, smem, s);
-  return a.dw_mode ? launch_t<__half, true>(a, tin, tout, tres, grid, smem, s) : launch_t<__half, false>(a, tin, tout, tres, grid, smem, s);
+#define EMD_DISPATCH(TT)                                                                                                   \
+  (a.dw_mode ? (a.has_res ? launch_t<TT, true, true>(a, tin, tout, tres, grid, smem, s)                                    \
+                          : launch_t<TT, true, false>(a, tin, tout, tres, grid, smem, s))                                  \
+             : (a.has_res ? launch_t<TT, false, true>(a, tin, tout, tres, grid, smem, s)                                   \
+                          : launch_t<TT, false, false>(a, tin, tout, tres, grid, smem, s)))
+  if (bf16) return EMD_DISPATCH(__nv_bfloat16);
+  return EMD_DISPATCH(__half);
+#undef EMD_DISPATCH
 }
 
 }  // namespace emd

@@ -159,6 +159,13 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
         "l"(*reinterpret_cast<unsigned long long*>(&c)));
   return *reinterpret_cast<float2*>(&d);
 }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
 }  // namespace ptx
 #endif
 

@@ -121,3 +121,36 @@ def test_tensor_core_shapes_s96_and_ragged_batch(setup):
     print("S=96: bf16 vs oracle", rel_l2(out, ref), "tcgen05 vs CUDA-core", rel_l2(out, out_cc))
     assert rel_l2(out, out_cc) <= 3e-2
     assert rel_l2(out, ref) <= 1.5e-1
+
+
+def test_wide_layers_block_tiled_s256(emd):
+    """256x256 crops: the 728-channel trunk is a 16x16 map, so the middle flow, the ASPP branches (three N tiles,
+    dilated taps partly / wholly outside the map, the 3640-channel pellet) and every encoder/decoder layer run on the
+    block-tiled tcgen05 kernel (emd_fused.cu), incl. its depthwise-producer mode.  Each layer against the FP64 oracle
+    and against the CUDA-core kernel with the same 16-bit operand values."""
+    from oracle.weights import make_w1
+    S2 = 256
+    rng = np.random.default_rng(4321)
+    crops = rng.random((1, S2, S2)).astype(np.float32)
+    w1 = make_w1(crops, seed=3)
+    eng = emd.Engine(cropsize=S2, max_batch=1)
+    eng.load_weights(emd.weights.pack(w1))
+    ref, acts = oracle_acts(w1, crops)
+    bad = []
+    for layer, (i, r, o) in layer_io_table().items():
+        res = None if r is None else acts[r]
+        eng.set_tensor_cores(True)
+        got = eng.run_layer(layer, acts[i], res, mode="bf16")
+        eng.set_tensor_cores(False)
+        ab = eng.run_layer(layer, acts[i], res, mode="bf16")
+        eng.set_tensor_cores(True)
+        e_ab, e_or = rel_l2(got, ab), rel_l2(got, acts[o])
+        # aspp_image: pooled 8x8 map, BN statistics nearly degenerate (same exception as in test_every_layer_tensor_core)
+        if e_ab > 5e-4 or e_or > (2.5e-2 if layer == "aspp_image" else 7e-3):
+            bad.append((layer, e_ab, e_or))
+    assert not bad, f"layer, tcgen05-vs-CUDA-core, vs-oracle: {bad}"
+    out = eng.forward(crops, mode="bf16")
+    eng.set_tensor_cores(False)
+    out_cc = eng.forward(crops, mode="bf16")
+    print("S=256 end to end: bf16 vs oracle", rel_l2(out, ref), "tcgen05 vs CUDA-core", rel_l2(out, out_cc))
+    assert rel_l2(out, out_cc) <= 5e-2
