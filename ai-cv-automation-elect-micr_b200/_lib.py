@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libemd.so")
+LIB_PATH = os.environ.get("EMD_LIB") or os.path.join(_HERE, "libemd.so")   # EMD_LIB: A/B builds of the same ABI
 
 EMD_MODE_FP32, EMD_MODE_BF16, EMD_MODE_FP16 = 0, 1, 2
 EMD_VARIANT_A, EMD_VARIANT_B = 0, 1

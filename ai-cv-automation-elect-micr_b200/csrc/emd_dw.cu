@@ -17,7 +17,8 @@ constexpr int kTH = 8, kTW = 16, kHaloH = kTH + 2, kHaloW = kTW + 2;
 constexpr int kChunk = 64;
 constexpr int kStageBytes = kHaloH * kHaloW * kChunk * 2;  // 23040
 constexpr int kStages = 4;
-constexpr int kMathThreads = 256;
+constexpr int kGroupWarps = 8;
+constexpr int kMathThreads = 2 * kGroupWarps * 32;   // two groups of 8 warps take alternate items
 
 struct DwTmaArgs {
   DwParams p;
@@ -30,31 +31,23 @@ struct DwTmaArgs {
 
 template <typename T> struct Up;
 template <> struct Up<__nv_bfloat16> {
-  static __device__ __forceinline__ void up8(const uint4& u, float* f) {
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
-  }
+  static __device__ __forceinline__ float2 up(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
   static __device__ __forceinline__ uint32_t pack(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
   }
 };
 template <> struct Up<__half> {
-  static __device__ __forceinline__ void up8(const uint4& u, float* f) {
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-      f[2 * i] = t.x; f[2 * i + 1] = t.y;
-    }
-  }
+  static __device__ __forceinline__ float2 up(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
   static __device__ __forceinline__ uint32_t pack(float a, float b) {
     __half2 v = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
   }
 };
 
+// Thread = 4 channels x 1 pixel column x 8 rows of an (8 x 16 pixel, 64-channel) item: 16 lanes read one 128-byte
+// halo pixel per LDS.64, the 3x3 window slides down the column in registers (FP32, packed FFMA2), and the same
+// 16 lanes write one full 128-byte output pixel.
 template <typename T, bool kReduce>
 __global__ void __launch_bounds__(kMathThreads + 32, 1) dw_tma_kernel(const __grid_constant__ DwTmaArgs a,
                                                                       const __grid_constant__ CUtensorMap tmap) {
@@ -66,103 +59,99 @@ __global__ void __launch_bounds__(kMathThreads + 32, 1) dw_tma_kernel(const __gr
   const uint32_t bar_full = ptx::smem_u32(bars), bar_empty = bar_full + 8u * kStages;
   const DwParams& p = a.p;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(bar_full + 8u * s, 1); ptx::mbar_init(bar_empty + 8u * s, kMathThreads); }
+    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(bar_full + 8u * s, 1); ptx::mbar_init(bar_empty + 8u * s, kGroupWarps); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmap);
   }
   __syncthreads();
+  const int my_items = (a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (threadIdx.x >= kMathThreads) {
     // ---------------- producer ----------------
     if (threadIdx.x == kMathThreads) {
-      int it = 0;
-      for (int item = blockIdx.x; item < a.items; item += gridDim.x, ++it) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int k = 0, item = blockIdx.x; k < my_items; ++k, item += gridDim.x) {
         const int tile = item / a.nchunks, c = item - tile * a.nchunks;
         const int n_img = tile / a.tiles_per_img;
         const int rem = tile - n_img * a.tiles_per_img;
         const int by = rem / a.tiles_x, bx = rem - by * a.tiles_x;
-        const int s = it % kStages;
-        ptx::mbar_wait(bar_empty + 8u * s, (uint32_t)(((it / kStages) & 1) ^ 1));
+        ptx::mbar_wait(bar_empty + 8u * s, ph ^ 1u);
         ptx::mbar_arrive_expect_tx(bar_full + 8u * s, kStageBytes);
         ptx::tma_load_4d(base + (uint32_t)s * kStageBytes, &tmap, c * kChunk, bx * kTW - 1, by * kTH - 1, n_img, bar_full + 8u * s);
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
     return;
   }
 
   // ---------------- math warps ----------------
-  const int tid = threadIdx.x;
-  const int q = tid & 7, col = (tid >> 3) & 15, half = tid >> 7;
-  int it = 0;
+  const int grp = threadIdx.x >> 8, tg = threadIdx.x & 255, lane = threadIdx.x & 31;
+  const int cq = tg & 15, col = tg >> 4;
   int cur_c = -1;
-  float w[9][8];
-  for (int item = blockIdx.x; item < a.items; item += gridDim.x, ++it) {
+  float2 w[9][2];
+  int s = grp % kStages;
+  uint32_t ph = (uint32_t)((grp / kStages) & 1);
+  for (int k = grp; k < my_items; k += 2) {
+    const int item = blockIdx.x + k * gridDim.x;
     const int tile = item / a.nchunks, c = item - tile * a.nchunks;
     const int n_img = tile / a.tiles_per_img;
     const int rem = tile - n_img * a.tiles_per_img;
     const int by = rem / a.tiles_x, bx = rem - by * a.tiles_x;
-    const int ch = c * kChunk + q * 8;
+    const int ch = c * kChunk + cq * 4;
     const bool ch_ok = ch < p.in.C;
-    if (c != cur_c) {  // this thread's 9 x 8 depthwise weights for the chunk
+    if (c != cur_c) {  // this thread's 9 x 4 depthwise weights for the chunk
       cur_c = c;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
-        if (ch_ok) {
-          w0 = __ldg(reinterpret_cast<const float4*>(p.w + t * p.in.C + ch));
-          w1 = __ldg(reinterpret_cast<const float4*>(p.w + t * p.in.C + ch + 4));
-        }
-        w[t][0] = w0.x; w[t][1] = w0.y; w[t][2] = w0.z; w[t][3] = w0.w;
-        w[t][4] = w1.x; w[t][5] = w1.y; w[t][6] = w1.z; w[t][7] = w1.w;
+        float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ch_ok) w0 = __ldg(reinterpret_cast<const float4*>(p.w + t * p.in.C + ch));
+        w[t][0] = make_float2(w0.x, w0.y); w[t][1] = make_float2(w0.z, w0.w);
       }
     }
-    const int s = it % kStages;
-    ptx::mbar_wait(bar_full + 8u * s, (uint32_t)((it / kStages) & 1));
-    const uint8_t* hb = smem + (size_t)s * kStageBytes + q * 16;
-    // window rows: halo rows (4*half + i + ky), columns col..col+2
-    float win[3][3][8];
-    auto load_row = [&](int hy, float (&dst)[3][8]) {
+    ptx::mbar_wait(bar_full + 8u * s, ph);
+    const uint8_t* hb = smem + (size_t)s * kStageBytes + col * (kChunk * 2) + cq * 8;
+    float2 win[3][3][2];
+    auto load_row = [&](int hy, float2 (&dst)[3][2]) {
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const uint4 u = *reinterpret_cast<const uint4*>(hb + (size_t)(hy * kHaloW + col + kx) * (kChunk * 2));
-        Up<T>::up8(u, dst[kx]);
+        const uint2 u = *reinterpret_cast<const uint2*>(hb + (hy * kHaloW + kx) * (kChunk * 2));
+        dst[kx][0] = Up<T>::up(u.x); dst[kx][1] = Up<T>::up(u.y);
       }
     };
-    load_row(4 * half + 0, win[0]);
-    load_row(4 * half + 1, win[1]);
-    T* obase = reinterpret_cast<T*>(p.out.ptr) +
-               (((size_t)n_img * p.out.H + by * kTH + 4 * half) * p.out.W + bx * kTW + col) * p.out.pitch + p.out.coff + ch;
+    load_row(0, win[0]);
+    load_row(1, win[1]);
+    const size_t opix = ((size_t)n_img * p.out.H + by * kTH) * p.out.W + bx * kTW + col;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      load_row(4 * half + i + 2, win[(i + 2) % 3]);
-      float acc[8];
+    for (int i = 0; i < kTH; ++i) {
+      load_row(i + 2, win[(i + 2) % 3]);
+      float2 acc0 = ptx::fmul2(win[i % 3][0][0], w[0][0]), acc1 = ptx::fmul2(win[i % 3][0][1], w[0][1]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(win[(i + ky) % 3][kx][j], w[ky * 3 + kx][j], acc[j]);
+      for (int t = 1; t < 9; ++t) {
+        acc0 = ptx::ffma2(win[(i + t / 3) % 3][t % 3][0], w[t][0], acc0);
+        acc1 = ptx::ffma2(win[(i + t / 3) % 3][t % 3][1], w[t][1], acc1);
+      }
       if (kReduce) {
-        float t = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+        float t = (acc0.x + acc0.y) + (acc1.x + acc1.y);
         t += __shfl_xor_sync(0xffffffffu, t, 1);
         t += __shfl_xor_sync(0xffffffffu, t, 2);
-        t += __shfl_xor_sync(0xffffffffu, t, 4);   // the 8 lanes of a quarter-warp hold the 8 channel chunks
-        if (q == 0) {
+        t += __shfl_xor_sync(0xffffffffu, t, 4);
+        t += __shfl_xor_sync(0xffffffffu, t, 8);   // the 16 lanes of a half-warp hold the 16 channel quads of one pixel
+        if (cq == 0) {
           float v = fmaf(t, a.scale, a.shift);
           if (a.relu6) v = fminf(fmaxf(v, 0.f), 6.f);
           if (a.clip01) v = fminf(fmaxf(v, 0.f), 1.f);
-          reinterpret_cast<float*>(p.out.ptr)[((size_t)n_img * p.out.H + by * kTH + 4 * half + i) * p.out.W + bx * kTW + col] = v;
+          reinterpret_cast<float*>(p.out.ptr)[opix + (size_t)i * p.out.W] = v;
         }
       } else if (ch_ok) {
-        uint4 o;
-        o.x = Up<T>::pack(acc[0], acc[1]); o.y = Up<T>::pack(acc[2], acc[3]);
-        o.z = Up<T>::pack(acc[4], acc[5]); o.w = Up<T>::pack(acc[6], acc[7]);
-        *reinterpret_cast<uint4*>(obase + (size_t)i * p.out.W * p.out.pitch) = o;
+        T* op = reinterpret_cast<T*>(p.out.ptr) + (opix + (size_t)i * p.out.W) * p.out.pitch + p.out.coff + ch;
+        *reinterpret_cast<uint2*>(op) = make_uint2(Up<T>::pack(acc0.x, acc0.y), Up<T>::pack(acc1.x, acc1.y));
       }
     }
-    ptx::mbar_arrive(bar_empty + 8u * s);
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(bar_empty + 8u * s);
+    s += 2;
+    if (s >= kStages) { s -= kStages; ph ^= 1u; }
   }
 }
 

@@ -526,7 +526,7 @@ cudaError_t run_step(ExecCtx& c, int idx) {
         const Step* dws = (idx > 0 && e->steps[idx - 1].kind == SK_DW && e->steps[idx - 1].layer == s.layer) ? &e->steps[idx - 1] : nullptr;
         const Ref rin = dws ? dws->in : s.in;
         const Tensor& tin = e->tensors[rin.t];
-        if (tin.external && !(s.Cout & 7)) {
+        if (tin.external && !(s.Cout & 7) && !((s.Cout >> 3) & ((s.Cout >> 3) - 1))) {
           StemParams p{};
           View vin = make_view(c, rin);
           p.in = reinterpret_cast<const float*>(vin.ptr); p.IH = tin.H; p.IW = tin.W;

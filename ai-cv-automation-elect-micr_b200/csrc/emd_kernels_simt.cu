@@ -413,54 +413,72 @@ cudaError_t launch_avgpool(const PoolParams& p, int et, cudaStream_t s) {
 // DMG:396; residual0 = 1x1 stride-2 conv 1->128, DMG:407).  K = 1 "GEMMs" are outer products:
 // one thread = (output pixel, 8 output channels); 8 consecutive lanes write 128 contiguous bytes.
 // ---------------------------------------------------------------------------------------------
+// Two phases per block of 256 consecutive output pixels: (1) one thread per pixel computes d once into shared
+// memory; (2) the block streams the pixels x channels out as consecutive 16-byte chunks (a warp instruction
+// writes 512 contiguous bytes), each thread keeping the weights / scale / shift of its fixed 8-channel group.
 template <typename T>
 __global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
-  const int cg = p.out.C >> 3;
-  const long long total = (long long)p.N * p.out.H * p.out.W * cg;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int g = (int)(idx % cg);
-  long long pix = idx / cg;
-  const int ox = (int)(pix % p.out.W); pix /= p.out.W;
-  const int oy = (int)(pix % p.out.H);
-  const int n = (int)(pix / p.out.H);
-  const float* img = p.in + (size_t)n * p.IH * p.IW;
-  float d;
-  if (p.dw) {
-    d = 0.f;
+  __shared__ float s_d[256];
+  const int OW = p.out.W, OH = p.out.H;
+  const long long npix = (long long)p.N * OH * OW;
+  const long long pix0 = (long long)blockIdx.x * 256;
+  {
+    const long long pix = pix0 + threadIdx.x;
+    float d = 0.f;
+    if (pix < npix) {
+      const int ox = (int)(pix % OW);
+      const long long r = pix / OW;
+      const int oy = (int)(r % OH), n = (int)(r / OH);
+      const float* img = p.in + (size_t)n * p.IH * p.IW;
+      if (p.dw) {
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = oy - 1 + ky;
-      if (iy < 0 || iy >= p.IH) continue;
+        for (int ky = 0; ky < 3; ++ky) {
+          const int iy = oy - 1 + ky;
+          if (iy < 0 || iy >= p.IH) continue;
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = ox - 1 + kx;
-        if (ix < 0 || ix >= p.IW) continue;
-        d = fmaf(__ldg(img + (size_t)iy * p.IW + ix), p.dw[ky * 3 + kx], d);
+          for (int kx = 0; kx < 3; ++kx) {
+            const int ix = ox - 1 + kx;
+            if (ix < 0 || ix >= p.IW) continue;
+            d = fmaf(__ldg(img + (size_t)iy * p.IW + ix), p.dw[ky * 3 + kx], d);
+          }
+        }
+      } else {
+        d = __ldg(img + (size_t)(oy * p.istride) * p.IW + ox * p.istride);
       }
+      if (sizeof(T) == 2) d = to_f(from_f<T>(d));  // the GEMM A operand is 16-bit in the 16-bit modes
     }
-    if (sizeof(T) == 2) d = to_f(from_f<T>(d));  // the depthwise output is a 16-bit GEMM operand in the 16-bit modes
-  } else {
-    d = __ldg(img + (size_t)(oy * p.istride) * p.IW + ox * p.istride);
-    if (sizeof(T) == 2) d = to_f(from_f<T>(d));
+    s_d[threadIdx.x] = d;
   }
-  float w[8], sc[8], sh[8], o[8];
+  __syncthreads();
+  const int cg = p.out.C >> 3;                 // 8-channel groups per pixel (power of two: 8 or 16)
+  const int g = threadIdx.x & (cg - 1);
+  float w[8], sc[8], sh[8];
   VecIO<float, 8>::ld(p.w + g * 8, w);
   VecIO<float, 8>::ld(p.scale + g * 8, sc);
   VecIO<float, 8>::ld(p.shift + g * 8, sh);
+  const int ppi = 256 / cg;                    // pixels covered by one pass of the block
+  T* obase = reinterpret_cast<T*>(p.out.ptr);
+  for (int k = 0; k < cg; ++k) {
+    const int lp = k * ppi + (threadIdx.x / cg);
+    const long long pix = pix0 + lp;
+    if (pix >= npix) break;
+    const float d = s_d[lp];
+    float o[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float v = fmaf(w[j] * d, sc[j], sh[j]);
-    if (p.relu6) v = fminf(fmaxf(v, 0.f), 6.f);
-    o[j] = v;
+    for (int j = 0; j < 8; ++j) {
+      float v = fmaf(w[j] * d, sc[j], sh[j]);
+      if (p.relu6) v = fminf(fmaxf(v, 0.f), 6.f);
+      o[j] = v;
+    }
+    VecIO<T, 8>::st(obase + (size_t)pix * p.out.pitch + p.out.coff + g * 8, o);
   }
-  T* op = reinterpret_cast<T*>(p.out.ptr) + (((size_t)n * p.out.H + oy) * p.out.W + ox) * p.out.pitch + p.out.coff + g * 8;
-  VecIO<T, 8>::st(op, o);
 }
 
 cudaError_t launch_stem(const StemParams& p, int et, cudaStream_t s) {
-  const long long total = (long long)p.N * p.out.H * p.out.W * (p.out.C / 8);
-  const unsigned grid = (unsigned)((total + 255) / 256);
+  const long long npix = (long long)p.N * p.out.H * p.out.W;
+  const int cg = p.out.C >> 3;
+  if (cg < 1 || cg > 256 || (cg & (cg - 1))) return cudaErrorInvalidValue;
+  const unsigned grid = (unsigned)((npix + 255) / 256);
   if (et == ET_F32) stem_kernel<float><<<grid, 256, 0, s>>>(p);
   else if (et == ET_BF16) stem_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p);
   else stem_kernel<__half><<<grid, 256, 0, s>>>(p);
