@@ -41,6 +41,7 @@ SIGNATURES = {
     "emd_set_tensor_cores": (_I, [_P, _I]),
     "emd_set_profile": (_I, [_P, _I]),
     "emd_num_steps": (_I, [_P]),
+    "emd_step_launches": (_I, [_P, _I]),
     "emd_step_info": (_I, [_P, _I, C.c_char_p, _SZ, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

@@ -51,6 +51,9 @@ struct Step {
   float scale0 = 1.f, shift0 = 0.f;  // host copies of scale[0] / shift[0] (single-output-channel layers)
   float ms = 0.f;
   double flops = 0, bytes = 0;  // per crop: algorithmic FLOPs and (16-bit storage) HBM bytes
+  double in_bytes = 0;          // the part of `bytes` that is the read of the step's input
+  bool fused = false;           // last run: SK_DW computed inside the next step's GEMM kernel / SK_CONV that absorbed it
+  int nlaunch = 0;              // kernels launched for this step in the last run
 };
 
 struct BlobEntry { uint32_t rows, cols; size_t offset; };
@@ -74,6 +77,8 @@ struct emd_engine {
   int last_n = 0, last_et = 0;
   // staging for host I/O of emd_forward
   float *d_stage_in = nullptr, *d_stage_out = nullptr;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of emd_forward with host buffers
+  cudaEvent_t ev_in[2] = {}, ev_done[2] = {}, ev_out[2] = {}, ev_start = nullptr;
   // whole-image pipeline buffers (grown on demand)
   void* d_img_raw = nullptr; size_t img_raw_bytes = 0;
   float* d_img = nullptr; size_t img_bytes = 0;
@@ -255,7 +260,7 @@ void annotate_work(emd_engine* e) {
     const double in_b = ipx * s.in.C * (ti.external ? 4 : 2), out_b = opx * s.out.C * (to.external ? 4 : 2);
     const double res_b = s.res.t >= 0 ? opx * s.res.C * 2 : 0;
     switch (s.kind) {
-      case SK_DW: s.flops = 2.0 * 9 * opx * s.Cin; s.bytes = in_b + out_b; break;
+      case SK_DW: s.flops = 2.0 * 9 * opx * s.Cin; s.bytes = in_b + out_b; s.in_bytes = in_b; break;
       case SK_CONV: {
         double taps = 0;  // in-bounds taps summed over output pixels
         const int half = s.k / 2;
@@ -267,6 +272,7 @@ void annotate_work(emd_engine* e) {
           }
         s.flops = 2.0 * taps * s.Cin * s.Cout;
         s.bytes = in_b / (s.stride * s.stride) + out_b + res_b + 2.0 * s.k * s.k * s.Cin * s.Cout / e->max_batch;
+        s.in_bytes = in_b / (s.stride * s.stride);
         break;
       }
       case SK_DECONV:
@@ -492,15 +498,25 @@ bool dw_fusable(const ExecCtx& c, int conv_idx, ConvParams* out) {
   return true;
 }
 
+cudaError_t run_step_impl(ExecCtx& c, int idx);
 cudaError_t run_step(ExecCtx& c, int idx) {
+  Step& s = c.e->steps[idx];
+  const long long before = c.e->launches;
+  s.fused = false;
+  cudaError_t r = run_step_impl(c, idx);
+  s.nlaunch = (int)(c.e->launches - before);
+  return r;
+}
+
+cudaError_t run_step_impl(ExecCtx& c, int idx) {
   emd_engine* e = c.e;
   Step& s = e->steps[idx];
   const Tensor& ti = e->tensors[s.in.t];
   const Tensor& to = e->tensors[s.out.t];
   switch (s.kind) {
     case SK_DW: {
-      if (s.Cin == 1) return cudaSuccess;  // 1-channel stem: the depthwise is fused into the pointwise kernel below
-      if (dw_fusable(c, idx + 1, nullptr)) return cudaSuccess;  // computed inside the pointwise GEMM's producer warps
+      if (s.Cin == 1) { s.fused = true; return cudaSuccess; }  // 1-channel stem: the depthwise is fused into the pointwise kernel below
+      if (dw_fusable(c, idx + 1, nullptr)) { s.fused = true; return cudaSuccess; }  // computed inside the pointwise GEMM's producer warps
       DwParams p{};
       p.in = make_view(c, s.in); p.out = make_view(c, s.out);
       p.N = c.n; p.OH = to.H; p.OW = to.W; p.stride = s.stride; p.rate = s.rate;
@@ -535,11 +551,13 @@ cudaError_t run_step(ExecCtx& c, int idx) {
           p.w = (c.et != ET_F32 && s.wr[c.et]) ? s.wr[c.et] : s.w;
           p.scale = s.scale; p.shift = s.shift; p.istride = s.stride; p.relu6 = s.relu6;
           e->launches++;
+          s.fused = dws != nullptr;
           return launch_stem(p, c.et, c.s);
         }
       }
       ConvParams p{};
       if (dw_fusable(c, idx, &p)) {
+        s.fused = true;
         e->launches++;
         e->umma_launches++;
         return launch_conv_fused(p, c.et, e->steps[idx - 1].dw, e->num_sms, c.s);
@@ -690,6 +708,11 @@ int emd_destroy(emd_engine* e) {
                   e->d_partial, (void*)e->d_origins})
     if (p) cudaFree(p);
   for (auto ev : e->events) cudaEventDestroy(ev);
+  if (e->copy_in) {
+    cudaStreamDestroy(e->copy_in); cudaStreamDestroy(e->copy_out);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(e->ev_in[i]); cudaEventDestroy(e->ev_done[i]); cudaEventDestroy(e->ev_out[i]); }
+    cudaEventDestroy(e->ev_start);
+  }
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return EMD_OK;
@@ -731,20 +754,58 @@ int emd_forward(emd_engine* e, const float* crops, int n, float* out, int mode, 
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
   const bool in_dev = is_device_ptr(crops), out_dev = is_device_ptr(out);
   const size_t per = (size_t)e->S * e->S;
-  for (int c0 = 0; c0 < n; c0 += e->max_batch) {
-    const int nb = std::min(e->max_batch, n - c0);
+  if (in_dev && out_dev) {
+    for (int c0 = 0; c0 < n; c0 += e->max_batch) {
+      const int nb = std::min(e->max_batch, n - c0);
+      if ((rc = run_network(e, crops + c0 * per, out + c0 * per, nb, mode, s))) return rc;
+    }
+    return EMD_OK;
+  }
+  // Host buffers: the batch goes through in chunks of half the workspace so that the H2D copy of chunk i+1 and the
+  // D2H copy of chunk i-1 (copy streams) overlap the network pass of chunk i (compute stream).  The two halves of the
+  // staging buffers alternate; events order reuse.
+  const int ch = e->max_batch >= 16 ? e->max_batch / 2 : e->max_batch;
+  const int nslots = e->max_batch >= 16 ? 2 : 1;
+  const int nchunks = (n + ch - 1) / ch;
+  if (!e->copy_in) {
+    CU(e, cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking));
+    CU(e, cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CU(e, cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
+      CU(e, cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+      CU(e, cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
+    }
+    CU(e, cudaEventCreateWithFlags(&e->ev_start, cudaEventDisableTiming));
+  }
+  CU(e, cudaEventRecord(e->ev_start, s));          // work already queued on the caller's stream comes first
+  CU(e, cudaStreamWaitEvent(e->copy_in, e->ev_start, 0));
+  CU(e, cudaStreamWaitEvent(e->copy_out, e->ev_start, 0));
+  for (int i = 0; i < nchunks; ++i) {
+    const int c0 = i * ch, nb = std::min(ch, n - c0), slot = i % nslots;
     const float* d_in = crops + c0 * per;
     float* d_out = out + c0 * per;
     if (!in_dev) {
-      CU(e, cudaMemcpyAsync(e->d_stage_in, d_in, nb * per * 4, cudaMemcpyHostToDevice, s));
-      d_in = e->d_stage_in;
+      float* stage = e->d_stage_in + (size_t)slot * ch * per;
+      if (i >= nslots) CU(e, cudaStreamWaitEvent(e->copy_in, e->ev_done[slot], 0));   // pass i - nslots has read this slot
+      CU(e, cudaMemcpyAsync(stage, d_in, nb * per * 4, cudaMemcpyHostToDevice, e->copy_in));
+      CU(e, cudaEventRecord(e->ev_in[slot], e->copy_in));
+      CU(e, cudaStreamWaitEvent(s, e->ev_in[slot], 0));
+      d_in = stage;
     }
-    if (!out_dev) d_out = e->d_stage_out;
-    rc = run_network(e, d_in, d_out, nb, mode, s);
-    if (rc) return rc;
-    if (!out_dev) CU(e, cudaMemcpyAsync(out + c0 * per, d_out, nb * per * 4, cudaMemcpyDeviceToHost, s));
+    if (!out_dev) {
+      d_out = e->d_stage_out + (size_t)slot * ch * per;
+      if (i >= nslots) CU(e, cudaStreamWaitEvent(s, e->ev_out[slot], 0));              // D2H of pass i - nslots has drained this slot
+    }
+    if ((rc = run_network(e, d_in, d_out, nb, mode, s))) return rc;
+    CU(e, cudaEventRecord(e->ev_done[slot], s));
+    if (!out_dev) {
+      CU(e, cudaStreamWaitEvent(e->copy_out, e->ev_done[slot], 0));
+      CU(e, cudaMemcpyAsync(out + c0 * per, d_out, nb * per * 4, cudaMemcpyDeviceToHost, e->copy_out));
+      CU(e, cudaEventRecord(e->ev_out[slot], e->copy_out));
+    }
   }
-  if (!out_dev || !in_dev) CU(e, cudaStreamSynchronize(s));
+  CU(e, cudaStreamSynchronize(s));
+  if (!out_dev) CU(e, cudaStreamSynchronize(e->copy_out));
   return EMD_OK;
 }
 
@@ -1034,13 +1095,26 @@ int emd_set_profile(emd_engine* e, int on) {
 
 int emd_num_steps(const emd_engine* e) { return e ? (int)e->steps.size() : -1; }
 
+int emd_step_launches(const emd_engine* e, int idx) {
+  if (!e || idx < 0 || idx >= (int)e->steps.size()) return -1;
+  return e->steps[idx].nlaunch;
+}
+
 int emd_step_info(const emd_engine* e, int idx, char* name, size_t name_cap, float* ms, double* flops, double* bytes) {
   if (!e || idx < 0 || idx >= (int)e->steps.size()) return EMD_EINVAL;
   const Step& s = e->steps[idx];
   if (name && name_cap) { strncpy(name, s.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
   if (ms) *ms = s.ms;
-  if (flops) *flops = s.flops;
-  if (bytes) *bytes = s.bytes;
+  double fl = s.flops, by = s.bytes;
+  if (s.fused && s.kind == SK_DW) { fl = 0; by = 0; }   // accounted in the GEMM step that computed it
+  if (s.fused && s.kind == SK_CONV && idx > 0 && e->steps[idx - 1].kind == SK_DW && e->steps[idx - 1].layer == s.layer) {
+    // one kernel did depthwise + pointwise: it reads the depthwise INPUT once; the intermediate never reaches HBM
+    const Step& d = e->steps[idx - 1];
+    fl += d.flops;
+    by += d.in_bytes - s.in_bytes;
+  }
+  if (flops) *flops = fl;
+  if (bytes) *bytes = by;
   return EMD_OK;
 }
 

@@ -311,15 +311,13 @@ cudaError_t launch_dw3x3(const DwParams& p, int et, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 template <typename T, int V>
 __global__ void __launch_bounds__(256) resize_kernel(const ResizeParams p) {
+  // thread = (output pixel, V channels); blockIdx.y = output row, blockIdx.z = image: the row's two source rows and vertical
+  // weight are block-uniform, consecutive threads walk the channels of consecutive pixels (coalesced 16-byte accesses)
   const int C = p.in.C, cg = C / V;
-  const long long total = (long long)p.N * p.out.H * p.out.W * cg;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int g = (int)(idx % cg);
-  long long pix = idx / cg;
-  const int ox = (int)(pix % p.out.W); pix /= p.out.W;
-  const int oy = (int)(pix % p.out.H);
-  const int n = (int)(pix / p.out.H);
+  const int oy = blockIdx.y, n = blockIdx.z;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.out.W * cg) return;
+  const int ox = idx / cg, g = idx - ox * cg;
   const float sy = oy * ((float)p.in.H / (float)p.out.H), sx = ox * ((float)p.in.W / (float)p.out.W);
   const int y0 = (int)floorf(sy), x0 = (int)floorf(sx);
   const int y1 = min(y0 + 1, p.in.H - 1), x1 = min(x0 + 1, p.in.W - 1);
@@ -348,12 +346,14 @@ static cudaError_t launch_resize_t(const ResizeParams& p, cudaStream_t s) {
   const int C = p.in.C;
   const bool al8 = ((C | p.in.pitch | p.in.coff | p.out.pitch | p.out.coff) & 7) == 0;
   const long long px = (long long)p.N * p.out.H * p.out.W;
+  (void)px;
+  if (p.N > 65535 || p.out.H > 65535) return cudaErrorInvalidValue;
   if (sizeof(T) == 2 && al8) {
-    long long total = px * (C / 8);
-    resize_kernel<T, 8><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
+    dim3 grid((unsigned)((p.out.W * (C / 8) + 255) / 256), (unsigned)p.out.H, (unsigned)p.N);
+    resize_kernel<T, 8><<<grid, 256, 0, s>>>(p);
   } else {
-    long long total = px * (C / 4);
-    resize_kernel<T, 4><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
+    dim3 grid((unsigned)((p.out.W * (C / 4) + 255) / 256), (unsigned)p.out.H, (unsigned)p.N);
+    resize_kernel<T, 4><<<grid, 256, 0, s>>>(p);
   }
   return cudaGetLastError();
 }

@@ -174,11 +174,11 @@ class Engine:
         self._check(self.lib.emd_set_profile(self.h, int(on)), "emd_set_profile")
 
     def step_info(self):
-        """[(name, ms, flops_per_crop, bytes_per_crop)] of the last profiled forward."""
+        """[(name, ms, flops_per_crop, bytes_per_crop, launches)] of the last profiled forward."""
         out = []
         name = C.create_string_buffer(64)
         ms, fl, by = C.c_float(), C.c_double(), C.c_double()
         for i in range(self.lib.emd_num_steps(self.h)):
             self.lib.emd_step_info(self.h, i, name, 64, C.byref(ms), C.byref(fl), C.byref(by))
-            out.append((name.value.decode(), ms.value, fl.value, by.value))
+            out.append((name.value.decode(), ms.value, fl.value, by.value, int(self.lib.emd_step_launches(self.h, i))))
         return out

@@ -64,6 +64,18 @@ def peaks():
     return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def measured_traffic(layer, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel that runs `layer`, from the committed
+    `ncu --set full` capture (profiles/traffic.json, written by tools/ncu_traffic.py), scaled to this batch."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p)).get(layer)
+    if not d:
+        return None
+    return d["dram_bytes_per_launch"] * batch / d["batch"]
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
@@ -251,35 +263,28 @@ def main():
         info = eng.step_info()
         eng.set_profile(False)
         tot_ms = sum(i[1] for i in info)
-        name, kms, fl, by = max(info, key=lambda i: i[1])
-        fl, by = fl * B, by * B
+        # dominant kernel = the step with the largest device time; a step is one kernel launch, except the
+        # transposed convs (4 sub-pixel phase launches of the same kernel): per-launch figures divide by `launches`
+        name, kms, fl, by, nl = max(info, key=lambda i: i[1])
+        nl = max(nl, 1)
+        fl, by = fl * B / nl, by * B / nl          # algorithmic work of ONE launch (whole batch)
+        lms = kms / nl                              # average launch duration (CUDA events on the launching stream)
         t_tensor, t_hbm = fl / (pk["tflops"] * 1e12), by / (pk["hbm_gbs"] * 1e9)
         if t_tensor >= t_hbm:
-            roof = {"bound": "tensor", "achieved": fl / (kms * 1e-3) / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s"}
+            roof = {"bound": "tensor", "achieved": fl / (lms * 1e-3) / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s"}
         else:
-            roof = {"bound": "hbm", "achieved": by / (kms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s"}
+            roof = {"bound": "hbm", "achieved": by / (lms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
-        roof["traffic"] = None
+        roof["traffic"] = measured_traffic(name, B)
         roof["kernel"] = name
-        roof["kernel_ms"] = kms
+        roof["launches_per_step"] = nl
+        roof["kernel_ms"] = lms
         roof["kernel_share_of_step"] = kms / tot_ms
-        roof["peak_source"] = pk["source"]
-        # whole-network roofline with per-layer fusion: sum over layers of
-        # max(FLOPs/P_tensor, bytes/BW_hbm); a separable block counts as ONE unit whose depthwise
-        # intermediate never leaves the SM (its write + re-read are not algorithmic bytes)
-        def fused_units(steps):
-            units, k = [], 0
-            while k < len(steps):
-                n, _, fl, by = steps[k]
-                if n.endswith(":dw") and k + 1 < len(steps) and steps[k + 1][0] == n[:-3]:
-                    mid = by / 5.0 if n[:-3].endswith("_strided") else by / 2.0   # bytes of the dw output
-                    units.append((fl + steps[k + 1][2], by - mid + steps[k + 1][3] - mid))
-                    k += 2
-                else:
-                    units.append((fl, by))
-                    k += 1
-            return units
-        t_roof = sum(max(fl * B / (pk["tflops"] * 1e12), by * B / (pk["hbm_gbs"] * 1e9)) for fl, by in fused_units(info))
+        roof["peak_source"] = pk["source"] + " (sustained BF16 figure: the kernel is timed inside a long step)"
+        # whole-network roofline with per-layer fusion: sum over steps of max(FLOPs/P_tensor, bytes/BW_hbm)
+        # with the ALGORITHMIC bytes of the steps as they ran (depthwise computed inside a GEMM kernel: its
+        # intermediate is not counted)
+        t_roof = sum(max(f * B / (pk["tflops"] * 1e12), b * B / (pk["hbm_gbs"] * 1e9)) for _, _, f, b, n_ in info if n_ > 0)
         roof["network_roofline_ms"] = t_roof * 1e3
         roof["network_frac"] = t_roof * 1e3 / (ms / args.steps)
         top = sorted(info, key=lambda i: -i[1])[:8]

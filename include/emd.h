@@ -121,8 +121,12 @@ int emd_set_tensor_cores(emd_engine* e, int on);
  * (needs emd_set_profile(e,1); serialises the stream) */
 int emd_set_profile(emd_engine* e, int on);
 int emd_num_steps(const emd_engine* e);
+/* flops / bytes: ALGORITHMIC work per crop of the step as it ran last (a depthwise step computed inside the
+ * next step's GEMM kernel reports 0 and the GEMM step reports depthwise input + its own output) */
 int emd_step_info(const emd_engine* e, int idx, char* name, size_t name_cap, float* ms,
                   double* flops, double* bytes);
+/* kernels launched for step idx in the last forward (a transposed conv is 4 sub-pixel phase launches) */
+int emd_step_launches(const emd_engine* e, int idx);
 
 #ifdef __cplusplus
 }

@@ -40,21 +40,24 @@ def main():
     for _ in range(reps):
         eng.forward(xd, out=out, mode=a.mode)
         info = eng.step_info()
-        acc = info if acc is None else [(i[0], i[1] + j[1], i[2], i[3]) for i, j in zip(acc, info)]
-    info = [(n, ms / reps, fl, by) for n, ms, fl, by in acc]
+        acc = info if acc is None else [(i[0], i[1] + j[1], i[2], i[3], i[4]) for i, j in zip(acc, info)]
+    info = [(n, ms / reps, fl, by, nl) for n, ms, fl, by, nl in acc]
     tot = sum(i[1] for i in info)
     B = a.batch
     lines = [f"# per-step device time, batch {B} x {a.crop}^2, mode {a.mode}, CUDA events, mean of {reps}; "
              f"peaks: HBM {pk['hbm_gbs']} GB/s, tensor {pk['bf16_tflops_sustained']} TFLOP/s",
-             f"{'step':20s} {'ms':>8s} {'share':>6s} {'GB/s':>8s} {'%hbm':>6s} {'TFLOP/s':>8s} {'%tc':>6s} {'roof_ms':>8s}"]
+             "# bytes / FLOPs are algorithmic per step as it ran (a separable block whose depthwise runs inside the GEMM kernel is one step)",
+             f"{'step':20s} {'ms':>8s} {'share':>6s} {'GB/s':>8s} {'%hbm':>6s} {'TFLOP/s':>8s} {'%tc':>6s} {'roof_ms':>8s} {'launches':>8s}"]
     roof_tot = 0.0
-    for n, ms, fl, by in info:
+    for n, ms, fl, by, nl in info:
+        if nl == 0:
+            continue   # computed inside the next step's kernel
         gbs = by * B / (ms * 1e-3) / 1e9 if ms > 0 else 0
         tf = fl * B / (ms * 1e-3) / 1e12 if ms > 0 else 0
         roof = max(by * B / (pk["hbm_gbs"] * 1e9), fl * B / (pk["bf16_tflops_sustained"] * 1e12)) * 1e3
         roof_tot += roof
         lines.append(f"{n:20s} {ms:8.3f} {100 * ms / tot:5.1f}% {gbs:8.0f} {100 * gbs / pk['hbm_gbs']:5.1f}% {tf:8.1f} "
-                     f"{100 * tf / pk['bf16_tflops_sustained']:5.1f}% {roof:8.3f}")
+                     f"{100 * tf / pk['bf16_tflops_sustained']:5.1f}% {roof:8.3f} {nl:8d}")
     lines.append(f"{'TOTAL':20s} {tot:8.3f} ms -> {B / tot * 1e3:.0f} crops/s; roofline {roof_tot:.3f} ms "
                  f"({B / roof_tot * 1e3:.0f} crops/s); fraction {roof_tot / tot:.3f}")
     text = "\n".join(lines)
