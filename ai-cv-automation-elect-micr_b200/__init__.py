@@ -4,3 +4,4 @@ CUDA behind a C ABI.  See DESIGN.md."""
 from .denoiser import Denoiser, scale0to1  # noqa: F401
 from .engine import Engine  # noqa: F401
 from . import weights  # noqa: F401
+from . import sharding  # noqa: F401

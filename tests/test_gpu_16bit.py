@@ -154,3 +154,21 @@ def test_wide_layers_block_tiled_s256(emd):
     out_cc = eng.forward(crops, mode="bf16")
     print("S=256 end to end: bf16 vs oracle", rel_l2(out, ref), "tcgen05 vs CUDA-core", rel_l2(out, out_cc))
     assert rel_l2(out, out_cc) <= 5e-2
+
+
+def test_full_size_batch_properties(emd):
+    """BASELINE.json's full crop size (512x512, batch 16), size-independent properties: outputs finite and in [0,1]
+    (in-graph clip, DMG:534-538), a crop's result does not depend on its batch neighbours or its position in the
+    batch, and host-buffer (chunked, copy-overlapped) and device-buffer calls give the same bits."""
+    import torch
+    rng = np.random.default_rng(99)
+    crops = rng.random((16, 512, 512)).astype(np.float32)
+    eng = emd.Engine(cropsize=512, max_batch=16)
+    eng.load_weights(emd.weights.pack(emd.weights.init_reference_weights(1)))
+    a = eng.forward(crops, mode="bf16")
+    assert np.isfinite(a).all() and a.min() >= 0 and a.max() <= 1
+    c = eng.forward(crops[5:6], mode="bf16")
+    np.testing.assert_array_equal(c[0], a[5])
+    d = eng.forward(torch.from_numpy(crops[::-1].copy()).cuda(), mode="bf16")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d.cpu().numpy()[::-1], a)
