@@ -65,6 +65,7 @@ struct FusedArgs {
   int b_stage_bytes, nchunks, w_kblocks, m_tiles, tiles_x, tiles_per_img;
   int tmem_cols, acc_stride;
   int has_res;
+  int b_res;                 // taps mode: every B block of the launch stays in shared memory, loaded once per CTA (block = tap*nchunks + chunk)
   FastDiv d_nt, d_tpi, d_tx, d_chunks;   // by nt.nt, tiles_per_img, tiles_x, nchunks
   const float* dw_w;         // [9][Cin] FP32, tap-major (dw mode)
 };
@@ -240,15 +241,21 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
           }
         } else {
           const int xb = x0 * p.istride, yb = y0 * p.istride;
+          if (a.b_res && tile == (int)blockIdx.x) {   // first tile of this CTA: bring in every weight block, once
+            mbar_arrive_expect_tx(bar_bfull, bytes * (uint32_t)kblocks);
+            for (int t = 0; t < p.ntaps; ++t)
+              for (int c = 0; c < a.nchunks; ++c)
+                bulk_g2s(sB + (uint32_t)(t * a.nchunks + c) * a.b_stage_bytes, tbase + (size_t)(p.wrow[t] * a.nchunks + c) * bytes, bytes, bar_bfull);
+          }
           for (int t = 0; t < p.ntaps; ++t) {
             const char* wsrc = tbase + (size_t)(p.wrow[t] * a.nchunks) * bytes;
             const int xt = xb + p.dx[t], yt = yb + p.dy[t];
             for (int c = 0; c < a.nchunks; ++c) {
               mbar_wait(bar_aempty + 8u * ra.idx, ra.phase ^ 1u);
               const uint32_t bar = bar_afull + 8u * ra.idx;
-              mbar_arrive_expect_tx(bar, bytes + (uint32_t)kAStageBytes);
+              mbar_arrive_expect_tx(bar, (a.b_res ? 0u : bytes) + (uint32_t)kAStageBytes);
               tma_load_4d(sA + (uint32_t)ra.idx * kAStageBytes, &tmap_in, c * kBK, xt, yt, n_img, bar);
-              bulk_g2s(sB + (uint32_t)ra.idx * a.b_stage_bytes, wsrc, bytes, bar);
+              if (!a.b_res) bulk_g2s(sB + (uint32_t)ra.idx * a.b_stage_bytes, wsrc, bytes, bar);
               wsrc += bytes;
               ra.advance(1);
             }
@@ -270,9 +277,10 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
       mbar_wait(bar_tempty + 8u * acc, (uint32_t)(((tcount >> 1) & 1) ^ 1));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.acc_stride);
+      if (!kDw && a.b_res && tcount == 0) mbar_wait(bar_bfull, 0u);   // resident weights have landed
       int c = 0;
       for (int kb = 0; kb < kblocks; ++kb) {
-        const int sa = ra.idx, sb = kDw ? rb.idx : sa;
+        const int sa = ra.idx, sb = kDw ? rb.idx : (a.b_res ? kb : sa);
         mbar_wait(bar_afull + 8u * sa, ra.phase);
         if (kDw) mbar_wait(bar_bfull + 8u * sb, rb.phase);
         tc_fence_after();
@@ -522,6 +530,17 @@ cudaError_t launch_conv_fused(const ConvParams& p, int et, const float* dw, int 
       if (a.ring == 3 && a.SA <= 4) { a.ring = 2; continue; }
       if (a.SA > 2) { --a.SA; a.SB = a.SA; continue; }
       return cudaErrorInvalidValue;
+    }
+    // resident weights: when every B block of the launch fits next to >= 3 A stages, load them once per CTA instead of
+    // once per tile -- the per-tile traffic into the SM drops to the A tiles alone
+    const int nblocks = p.ntaps * a.nchunks;
+    if (a.nt.nt == 1 && nblocks <= 24) {
+      FusedArgs b = a;
+      b.b_res = 1; b.SB = nblocks; b.SA = kMaxStages; b.ring = kMaxRing;
+      while (fused_smem_bytes(b) > (size_t)kSmemLimit && (b.SA > 3 || b.ring > 2)) {
+        if (b.SA > 3) --b.SA; else --b.ring;
+      }
+      if (fused_smem_bytes(b) <= (size_t)kSmemLimit) a = b;
     }
   }
   const bool bf16 = et == ET_BF16;

@@ -10,6 +10,17 @@ from . import _lib
 from ._lib import MODES
 
 
+def _stream_for(x, stream):
+    """CUDA stream to launch on: the caller's, else torch's current stream when the buffer is a torch CUDA tensor (so the
+    call is ordered after the work that produced it), else None = the engine's own stream."""
+    if stream:
+        return C.c_void_p(stream)
+    if hasattr(x, "is_cuda") and x.is_cuda:
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    return None
+
+
 def _ptr(x):
     """Raw address of a numpy array or a torch tensor (host or CUDA)."""
     if isinstance(x, np.ndarray):
@@ -60,8 +71,8 @@ class Engine:
             else:
                 import torch
                 out = torch.empty((n, self.S, self.S), dtype=torch.float32, device=crops.device)
-        self._check(self.lib.emd_forward(self.h, _ptr(crops), n, _ptr(out), MODES[mode],
-                                         C.c_void_p(stream) if stream else None), "emd_forward")
+        self._check(self.lib.emd_forward(self.h, _ptr(crops), n, _ptr(out), MODES[mode], _stream_for(crops, stream)),
+                    "emd_forward")
         return out
 
     def run_layer(self, name, x, res=None, mode="fp32"):
@@ -155,7 +166,7 @@ class Engine:
         flags = (_lib.EMD_FLAG_PREPROCESS if preprocess else 0) | (_lib.EMD_FLAG_POSTPROCESS if postprocess else 0) \
             | (_lib.EMD_FLAG_INPUT_F64 if f64 else 0)
         self._check(self.lib.emd_denoise_image(self.h, _ptr(img), H, W, overlap, flags, MODES[mode], _ptr(out),
-                                               None), "emd_denoise_image")
+                                               _stream_for(img, None)), "emd_denoise_image")
         return out
 
     # -- measurement ---------------------------------------------------------------------------
