@@ -296,6 +296,10 @@ int plan_arena(emd_engine* e) {
       e->tensors[t].first = std::min(e->tensors[t].first, i);
       e->tensors[t].last = std::max(e->tensors[t].last, i);
     }
+    // a depthwise step may be computed INSIDE the next step's GEMM kernel (emd_fused.cu, dw mode): its input is then read
+    // while that step's output is being written, so the input must stay live (un-aliased) through the next step
+    if (s.kind == SK_DW && i + 1 < (int)e->steps.size() && e->steps[i + 1].layer == s.layer)
+      e->tensors[s.in.t].last = std::max(e->tensors[s.in.t].last, i + 1);
   }
   std::vector<int> order;
   for (int i = 0; i < (int)e->tensors.size(); ++i) {
@@ -569,9 +573,11 @@ cudaError_t run_step_impl(ExecCtx& c, int idx) {
     case SK_DECONV: {
       // conv2d_transpose 3x3 stride 2 SAME = 4 sub-pixel phases (App. A.4):
       //   out[2j+0] = in[j] w[0] + in[j-1] w[2];  out[2j+1] = in[j] w[1]   (per axis)
+      ConvParams ph[4];
       for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px) {
-          ConvParams p{};
+          ConvParams& p = ph[py * 2 + px];
+          p = ConvParams{};
           p.in = make_view(c, s.in); p.out = make_view(c, s.out);
           p.N = c.n; p.MH = ti.H; p.MW = ti.W;
           p.istride = 1; p.ostride = 2; p.oy0 = py; p.ox0 = px;
@@ -587,9 +593,16 @@ cudaError_t run_step_impl(ExecCtx& c, int idx) {
               p.wrow[p.ntaps] = kys[py][a] * 3 + kys[px][b2]; p.ntaps++;
             }
           }
-          cudaError_t r = run_conv(c, p, s);
-          if (r != cudaSuccess) return r;
         }
+      if (c.et != ET_F32 && e->use_umma && s.w16[c.et] && fused_multi_supported(ph, 4, c.et)) {
+        e->launches++;
+        e->umma_launches++;
+        return launch_conv_fused_multi(ph, 4, c.et, e->num_sms, c.s);   // one launch: work items = (input tile, phase)
+      }
+      for (int v = 0; v < 4; ++v) {
+        cudaError_t r = run_conv(c, ph[v], s);
+        if (r != cudaSuccess) return r;
+      }
       return cudaSuccess;
     }
   }

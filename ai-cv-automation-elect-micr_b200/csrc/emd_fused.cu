@@ -65,6 +65,12 @@ struct FusedArgs {
   int b_stage_bytes, nchunks, w_kblocks, m_tiles, tiles_x, tiles_per_img;
   int tmem_cols, acc_stride;
   int has_res;
+  // variants (taps mode): work items are (M tile, N tile, variant); a variant has its own tap list and its own output
+  // tensor map -- the 4 sub-pixel phases of a transposed conv run as ONE launch, neighbouring CTAs working on the phases
+  // of the same input tile at the same time, so the input comes from HBM once (the other phases hit L2)
+  int nvar;
+  int v_ntaps[4];
+  int v_dy[4][9], v_dx[4][9], v_wrow[4][9];
   int b_res;                 // taps mode: every B block of the launch stays in shared memory, loaded once per CTA (block = tap*nchunks + chunk)
   FastDiv d_nt, d_tpi, d_tx, d_chunks;   // by nt.nt, tiles_per_img, tiles_x, nchunks
   const float* dw_w;         // [9][Cin] FP32, tap-major (dw mode)
@@ -159,10 +165,12 @@ __device__ __forceinline__ void epi_half(const uint32_t (&v)[32], const float* _
   }
 }
 
+struct OutMaps { CUtensorMap m[4]; };   // output tensor map per variant
+
 template <typename T, bool kDw, bool kRes>
 __global__ void __launch_bounds__(kDw ? kBaseThreads + kMathThreads : kBaseThreads, 1)
 fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ CUtensorMap tmap_in,
-                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res) {
+                  const __grid_constant__ OutMaps tmaps_out, const __grid_constant__ CUtensorMap tmap_res) {
   extern __shared__ uint8_t smem_raw[];
   const ConvParams& p = a.p;
   const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -186,8 +194,15 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 * kMaxStages + 4 + kMaxRing);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = a.m_tiles * a.nt.nt;
-  const int kblocks = p.ntaps * a.nchunks;
+  const int total_tiles = a.m_tiles * a.nt.nt * a.nvar;
+  // work item -> (M tile, N tile, variant), variant fastest
+  auto split = [&](int item, int& mt, int& ntile, int& var) {
+    int q = item;
+    var = 0;
+    if (a.nvar > 1) { q = item >> 2; var = item & 3; }     // nvar is 1 or 4
+    mt = (int)fdiv((uint32_t)q, a.d_nt);
+    ntile = q - mt * a.nt.nt;
+  };
 
   for (int i = threadIdx.x; i < kMaxC; i += blockDim.x) {
     s_scale[i] = i < p.Cout ? p.scale[i] : 0.f;
@@ -206,7 +221,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
     for (int i = 0; i < kMaxRing; ++i) mbar_init(bar_rfull + 8u * i, 1);
     fence_barrier_init();
     prefetch_tmap(&tmap_in);
-    prefetch_tmap(&tmap_out);
+    for (int v = 0; v < a.nvar; ++v) prefetch_tmap(&tmaps_out.m[v]);
     if (kRes) prefetch_tmap(&tmap_res);
   }
   if (warp == 4) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
@@ -221,14 +236,16 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
       const char* wbase = reinterpret_cast<const char*>(p.w16);
       Ring ra(0, SA), rb(0, SB), rh(0, kDw ? SH : 1);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = (int)fdiv((uint32_t)tile, a.d_nt), ntile = tile - mt * a.nt.nt;
+        int mt, ntile, var;
+        split(tile, mt, ntile, var);
+        const int ntaps = a.v_ntaps[var];
         const uint32_t bytes = (uint32_t)a.nt.rows[ntile] * 128u;
         // packed weights: [n_tile][weight k-block = tap*nchunks + chunk][rows x 128 B, swizzled]
         const char* tbase = wbase + (size_t)a.nt.rows_before[ntile] * a.w_kblocks * 128;
         int n_img, y0, x0;
         tile_coords(a, mt, n_img, y0, x0);
         if (kDw) {
-          const char* wsrc = tbase + (size_t)(p.wrow[0] * a.nchunks) * bytes;
+          const char* wsrc = tbase + (size_t)(a.v_wrow[0][0] * a.nchunks) * bytes;
           for (int c = 0; c < a.nchunks; ++c) {
             mbar_wait(bar_hempty + 8u * rh.idx, rh.phase ^ 1u);
             mbar_arrive_expect_tx(bar_hfull + 8u * rh.idx, kHaloBytes);
@@ -242,14 +259,14 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
         } else {
           const int xb = x0 * p.istride, yb = y0 * p.istride;
           if (a.b_res && tile == (int)blockIdx.x) {   // first tile of this CTA: bring in every weight block, once
-            mbar_arrive_expect_tx(bar_bfull, bytes * (uint32_t)kblocks);
-            for (int t = 0; t < p.ntaps; ++t)
+            mbar_arrive_expect_tx(bar_bfull, bytes * (uint32_t)(ntaps * a.nchunks));
+            for (int t = 0; t < ntaps; ++t)
               for (int c = 0; c < a.nchunks; ++c)
-                bulk_g2s(sB + (uint32_t)(t * a.nchunks + c) * a.b_stage_bytes, tbase + (size_t)(p.wrow[t] * a.nchunks + c) * bytes, bytes, bar_bfull);
+                bulk_g2s(sB + (uint32_t)(t * a.nchunks + c) * a.b_stage_bytes, tbase + (size_t)(a.v_wrow[0][t] * a.nchunks + c) * bytes, bytes, bar_bfull);
           }
-          for (int t = 0; t < p.ntaps; ++t) {
-            const char* wsrc = tbase + (size_t)(p.wrow[t] * a.nchunks) * bytes;
-            const int xt = xb + p.dx[t], yt = yb + p.dy[t];
+          for (int t = 0; t < ntaps; ++t) {
+            const char* wsrc = tbase + (size_t)(a.v_wrow[var][t] * a.nchunks) * bytes;
+            const int xt = xb + a.v_dx[var][t], yt = yb + a.v_dy[var][t];
             for (int c = 0; c < a.nchunks; ++c) {
               mbar_wait(bar_aempty + 8u * ra.idx, ra.phase ^ 1u);
               const uint32_t bar = bar_afull + 8u * ra.idx;
@@ -269,7 +286,9 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
     int tcount = 0;
     const int last_ksteps = (p.Cin - (a.nchunks - 1) * kBK + 15) >> 4;   // K=16 steps of the last (possibly partial) chunk
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const int ntile = tile - (int)fdiv((uint32_t)tile, a.d_nt) * a.nt.nt;
+      int mt_unused, ntile, var;
+      split(tile, mt_unused, ntile, var);
+      const int kblocks = a.v_ntaps[var] * a.nchunks;
       const uint32_t n = (uint32_t)a.nt.rows[ntile];
       // instruction descriptor: D = F32 (bits 4-5), A/B format (bits 7-9 / 10-12), K-major A and B, N>>3 at 17-22, M>>4 at 24-28
       const uint32_t idesc = (1u << 4) | (Cv<T>::kFmt << 7) | (Cv<T>::kFmt << 10) | ((n >> 3) << 17) | ((kBM >> 4) << 24);
@@ -309,7 +328,8 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
     int pf_tile = blockIdx.x, pf_slab = 0, pf_buf = 0;
     auto prefetch_res = [&]() {
       if (pf_tile < total_tiles) {
-        const int mt = (int)fdiv((uint32_t)pf_tile, a.d_nt), ntile = pf_tile - mt * a.nt.nt;
+        int mt, ntile, var;
+        split(pf_tile, mt, ntile, var);
         int n_img, y0, x0;
         tile_coords(a, mt, n_img, y0, x0);
         mbar_arrive_expect_tx(bar_rfull + 8u * pf_buf, kSlabBytes);
@@ -323,7 +343,8 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
     int tcount = 0;
     Ring rq(0, R);                           // output staging slab
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const int mt = (int)fdiv((uint32_t)tile, a.d_nt), ntile = tile - mt * a.nt.nt;
+      int mt, ntile, var;
+      split(tile, mt, ntile, var);
       const int n0 = a.nt.n0[ntile], n = a.nt.rows[ntile];
       int n_img, y0, x0;
       tile_coords(a, mt, n_img, y0, x0);
@@ -358,7 +379,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
         }
         named_bar_sync(1, kEpiThreads);
         if (tid == 0) {
-          tma_store_4d(&tmap_out, sO + (uint32_t)buf * kSlabBytes, n0 + j * 64, x0, y0, n_img);
+          tma_store_4d(&tmaps_out.m[var], sO + (uint32_t)buf * kSlabBytes, n0 + j * 64, x0, y0, n_img);
           bulk_commit();
           if (kRes) {                      // refill the slab stored one iteration ago with the residual of the slab R-1 ahead
             bulk_wait_read<1>();
@@ -448,7 +469,7 @@ size_t fused_smem_bytes(const FusedArgs& a) {
 }
 
 template <typename T, bool kDw, bool kRes>
-cudaError_t launch_t(const FusedArgs& a, const CUtensorMap& tin, const CUtensorMap& tout, const CUtensorMap& tres, int grid,
+cudaError_t launch_t(const FusedArgs& a, const CUtensorMap& tin, const OutMaps& tout, const CUtensorMap& tres, int grid,
                      size_t smem, cudaStream_t s) {
   static thread_local int attr_dev = -1;
   int dev = 0;
@@ -490,10 +511,38 @@ bool fused_supported(const ConvParams& p, int et, const float* dw) {
   return tma_encoder() != nullptr;
 }
 
+// The nvar (1 or 4) convolutions differ only in their tap lists and output offsets (the sub-pixel phases of one transposed conv)
+bool fused_multi_supported(const ConvParams* ps, int nvar, int et) {
+  if (nvar != 4) return false;
+  for (int v = 0; v < nvar; ++v) {
+    const ConvParams& q = ps[v];
+    if (!fused_supported(q, et, nullptr) || q.res.ptr || q.istride != 1) return false;
+    if (q.in.ptr != ps[0].in.ptr || q.out.ptr != ps[0].out.ptr || q.w16 != ps[0].w16 || q.Cin != ps[0].Cin || q.Cout != ps[0].Cout ||
+        q.MH != ps[0].MH || q.MW != ps[0].MW || q.N != ps[0].N || q.ostride != ps[0].ostride || q.relu6 != ps[0].relu6)
+      return false;
+  }
+  return true;
+}
+
+static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const float* dw, int num_sms, cudaStream_t s);
+
 cudaError_t launch_conv_fused(const ConvParams& p, int et, const float* dw, int num_sms, cudaStream_t s) {
+  return launch_impl(&p, 1, et, dw, num_sms, s);
+}
+cudaError_t launch_conv_fused_multi(const ConvParams* ps, int nvar, int et, int num_sms, cudaStream_t s) {
+  return launch_impl(ps, nvar, et, nullptr, num_sms, s);
+}
+
+static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const float* dw, int num_sms, cudaStream_t s) {
+  const ConvParams& p = ps[0];
   FusedArgs a;
   memset(&a, 0, sizeof a);
   a.p = p;
+  a.nvar = nvar;
+  for (int v = 0; v < nvar; ++v) {
+    a.v_ntaps[v] = ps[v].ntaps;
+    for (int t = 0; t < ps[v].ntaps && t < 9; ++t) { a.v_dy[v][t] = ps[v].dy[t]; a.v_dx[v][t] = ps[v].dx[t]; a.v_wrow[v][t] = ps[v].wrow[t]; }
+  }
   a.nt = make_ntiling(p.Cout);
   a.dw_mode = dw ? 1 : 0;
   a.dw_w = dw;
@@ -534,7 +583,7 @@ cudaError_t launch_conv_fused(const ConvParams& p, int et, const float* dw, int 
     // resident weights: when every B block of the launch fits next to >= 3 A stages, load them once per CTA instead of
     // once per tile -- the per-tile traffic into the SM drops to the A tiles alone
     const int nblocks = p.ntaps * a.nchunks;
-    if (a.nt.nt == 1 && nblocks <= 24) {
+    if (a.nt.nt == 1 && nvar == 1 && nblocks <= 24) {
       FusedArgs b = a;
       b.b_res = 1; b.SB = nblocks; b.SA = kMaxStages; b.ring = kMaxRing;
       while (fused_smem_bytes(b) > (size_t)kSmemLimit && (b.SA > 3 || b.ring > 2)) {
@@ -544,8 +593,10 @@ cudaError_t launch_conv_fused(const ConvParams& p, int et, const float* dw, int 
     }
   }
   const bool bf16 = et == ET_BF16;
-  CUtensorMap tin, tout, tres;
+  CUtensorMap tin, tres;
+  OutMaps tout;
   memset(&tres, 0, sizeof tres);
+  memset(&tout, 0, sizeof tout);
   void* in_base = reinterpret_cast<char*>(p.in.ptr) + (size_t)p.in.coff * 2;
   if (a.dw_mode) {
     if (!tma_encode_nhwc(&tin, bf16, in_base, p.Cin, p.in.W, p.in.H, p.N, p.in.pitch, kBK, kHaloW, kHaloH, 1, false))
@@ -555,21 +606,23 @@ cudaError_t launch_conv_fused(const ConvParams& p, int et, const float* dw, int 
                          p.istride, true))
       return cudaErrorInvalidValue;
   }
-  {  // output view on the virtual grid: pixel (my, mx) -> out pixel (my*ostride + oy0, mx*ostride + ox0)
-    const size_t sx = (size_t)p.ostride * p.out.pitch, sy = (size_t)p.ostride * p.out.W * p.out.pitch,
-                 sn = (size_t)p.out.H * p.out.W * p.out.pitch;
-    void* ob = reinterpret_cast<char*>(p.out.ptr) + (((size_t)p.oy0 * p.out.W + p.ox0) * p.out.pitch + p.out.coff) * 2;
-    if (!tma_encode_view(&tout, bf16, ob, p.Cout, p.MW, p.MH, p.N, sx, sy, sn, 64, kTW, kTH, true)) return cudaErrorInvalidValue;
-    if (a.has_res) {
-      const size_t rx = (size_t)p.ostride * p.res.pitch, ry = (size_t)p.ostride * p.res.W * p.res.pitch,
-                   rn = (size_t)p.res.H * p.res.W * p.res.pitch;
-      void* rb = reinterpret_cast<char*>(p.res.ptr) + (((size_t)p.oy0 * p.res.W + p.ox0) * p.res.pitch + p.res.coff) * 2;
-      if (!tma_encode_view(&tres, bf16, rb, p.Cout, p.MW, p.MH, p.N, rx, ry, rn, 64, kTW, kTH, true)) return cudaErrorInvalidValue;
-    }
+  for (int v = 0; v < nvar; ++v) {  // output view on the virtual grid: pixel (my, mx) -> out pixel (my*ostride + oy0, mx*ostride + ox0)
+    const ConvParams& q = ps[v];
+    const size_t sx = (size_t)q.ostride * q.out.pitch, sy = (size_t)q.ostride * q.out.W * q.out.pitch,
+                 sn = (size_t)q.out.H * q.out.W * q.out.pitch;
+    void* ob = reinterpret_cast<char*>(q.out.ptr) + (((size_t)q.oy0 * q.out.W + q.ox0) * q.out.pitch + q.out.coff) * 2;
+    if (!tma_encode_view(&tout.m[v], bf16, ob, q.Cout, q.MW, q.MH, q.N, sx, sy, sn, 64, kTW, kTH, true)) return cudaErrorInvalidValue;
+  }
+  if (a.has_res) {
+    const size_t rx = (size_t)p.ostride * p.res.pitch, ry = (size_t)p.ostride * p.res.W * p.res.pitch,
+                 rn = (size_t)p.res.H * p.res.W * p.res.pitch;
+    void* rb = reinterpret_cast<char*>(p.res.ptr) + (((size_t)p.oy0 * p.res.W + p.ox0) * p.res.pitch + p.res.coff) * 2;
+    if (!tma_encode_view(&tres, bf16, rb, p.Cout, p.MW, p.MH, p.N, rx, ry, rn, 64, kTW, kTH, true)) return cudaErrorInvalidValue;
   }
   const size_t smem = fused_smem_bytes(a);
-  const int total_tiles = a.m_tiles * a.nt.nt;
-  const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+  const int total_tiles = a.m_tiles * a.nt.nt * nvar;
+  int grid = total_tiles < num_sms ? total_tiles : num_sms;
+  if (nvar == 4 && !(grid & 3)) --grid;   // a CTA strides the item list by the grid size: keep it odd so every CTA sees all 4 phases (8/4/4/2 k-blocks)
 #define EMD_DISPATCH(TT)                                                                                                   \
   (a.dw_mode ? (a.has_res ? launch_t<TT, true, true>(a, tin, tout, tres, grid, smem, s)                                    \
                           : launch_t<TT, true, false>(a, tin, tout, tres, grid, smem, s))                                  \

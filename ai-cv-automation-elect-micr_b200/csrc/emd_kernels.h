@@ -122,6 +122,9 @@ size_t umma_pack_weights(const float* w, int ntaps, int Cin, int Cout, int et, v
 // depthwise-3x3 producer: dw = [9][Cin] FP32 weights, p.in = the depthwise input)
 bool fused_supported(const ConvParams& p, int et, const float* dw);
 cudaError_t launch_conv_fused(const ConvParams& p, int et, const float* dw, int num_sms, cudaStream_t s);
+// the 4 sub-pixel phases of one transposed conv (same input, weights, epilogue; different taps / output offsets) as ONE launch
+bool fused_multi_supported(const ConvParams* ps, int nvar, int et);
+cudaError_t launch_conv_fused_multi(const ConvParams* ps, int nvar, int et, int num_sms, cudaStream_t s);
 void fused_set_enabled(bool on);
 
 // emd_kernels_wrap.cu: whole-image wrapper kernels

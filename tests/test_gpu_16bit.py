@@ -172,3 +172,14 @@ def test_full_size_batch_properties(emd):
     d = eng.forward(torch.from_numpy(crops[::-1].copy()).cuda(), mode="bf16")
     torch.cuda.synchronize()
     np.testing.assert_array_equal(d.cpu().numpy()[::-1], a)
+    # workspace reuse must not change a bit: same pass with every activation in its own buffer (this caught an arena
+    # lifetime bug: a depthwise input aliased with the output of the GEMM kernel that computes the depthwise on the fly)
+    eng.set_keep_activations(True)
+    k = eng.forward(crops, mode="bf16")
+    eng.set_keep_activations(False)
+    np.testing.assert_array_equal(k, a)
+    # and the tcgen05 path against the CUDA-core path with the same 16-bit operand values, at full crop size
+    eng.set_tensor_cores(False)
+    cc = eng.forward(crops[:2], mode="bf16")
+    eng.set_tensor_cores(True)
+    assert rel_l2(a[:2], cc) <= 5e-2

@@ -1,24 +1,39 @@
-import sys, importlib, numpy as np, torch, os
+#!/usr/bin/env python
+"""Determinism / batch-invariance probe at BASELINE.json's crop size: repeats host-buffer (chunked, copy streams) and
+device-buffer passes in several orders and reports per-crop mismatch counts.  python tools/determinism_probe.py [mode] [iters]"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 emd = importlib.import_module("ai-cv-automation-elect-micr_b200")
+mode = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 rng = np.random.default_rng(99)
 crops = rng.random((16, 512, 512)).astype(np.float32)
 eng = emd.Engine(cropsize=512, max_batch=16)
 eng.load_weights(emd.weights.pack(emd.weights.init_reference_weights(1)))
-mode = sys.argv[1] if len(sys.argv) > 1 else "bf16"
-a = eng.forward(crops, mode=mode)                                   # host path: 2 chunks of 8
-d = eng.forward(torch.from_numpy(crops).cuda(), mode=mode); torch.cuda.synchronize(); d = d.cpu().numpy()   # one pass of 16
-d2 = eng.forward(torch.from_numpy(crops).cuda(), mode=mode); torch.cuda.synchronize(); d2 = d2.cpu().numpy()
-print(mode, "host-vs-dev mismatches per crop:", [(int((a[i] != d[i]).sum())) for i in range(16)])
-print(mode, "dev-vs-dev  mismatches per crop:", [(int((d2[i] != d[i]).sum())) for i in range(16)])
-# which layer first differs between an 8-batch and a 16-batch pass?
-eng.set_keep_activations(True)
-x16 = torch.from_numpy(crops).cuda()
-eng.forward(x16, mode=mode); torch.cuda.synchronize()
-names = ["cnn0","cnn0_last","enc0","cnn1","enc1","enc2","enc3","trunk4","trunk_mid0","trunk_mid5","trunk_mid10","aspp_1x1","aspp_r6","aspp_pellet","upsample4","deconv2_0","dec2","deconv2to1","deconv1_0","dec1","deconv1to0","deconv0_0","residual0_d","dec0"]
-A = {n: eng.activation(n).copy() for n in names}
-x8 = torch.from_numpy(crops[:8]).cuda()
-eng.forward(x8, mode=mode); torch.cuda.synchronize()
-for n in names:
-    b = eng.activation(n)
-    print(f"{n:14s} mismatches {(b != A[n][:8]).sum()} of {b.size}")
+ref = eng.forward(crops, mode=mode)
+rev = np.ascontiguousarray(crops[::-1])
+bad = 0
+for it in range(iters):
+    a = eng.forward(crops, mode=mode)
+    c = eng.forward(crops[5:6], mode=mode)
+    t = torch.from_numpy(rev).cuda()
+    d = eng.forward(t, mode=mode)
+    torch.cuda.synchronize()
+    d = d.cpu().numpy()[::-1]
+    t2 = torch.from_numpy(crops).cuda()
+    f = eng.forward(t2, mode=mode)
+    torch.cuda.synchronize()
+    f = f.cpu().numpy()
+    rows = {"host16": [int((a[i] != ref[i]).sum()) for i in range(16)], "single5": [int((c[0] != ref[5]).sum())],
+            "dev16rev": [int((d[i] != ref[i]).sum()) for i in range(16)], "dev16": [int((f[i] != ref[i]).sum()) for i in range(16)]}
+    for k, v in rows.items():
+        if any(v):
+            bad += 1
+            print(f"iter {it} {k}: mismatching elements per crop {v}")
+print("iterations", iters, "mismatching passes", bad)
