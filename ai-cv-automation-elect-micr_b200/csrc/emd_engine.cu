@@ -675,6 +675,8 @@ int emd_create(emd_engine** out, int device, int cropsize, int variant, int max_
   e->use_umma = !(env && env[0] == '1');
   env = getenv("EMD_DISABLE_TMA");
   umma_set_tma(!(env && env[0] == '1'));
+  env = getenv("EMD_DISABLE_PAIR");
+  fused_set_pair(!(env && env[0] == '1'));
   env = getenv("EMD_DISABLE_FUSED");
   fused_set_enabled(!(env && env[0] == '1'));
 #define CUC(call)                                                                                       \

@@ -65,6 +65,10 @@ struct FusedArgs {
   int b_stage_bytes, nchunks, w_kblocks, m_tiles, tiles_x, tiles_per_img;
   int tmem_cols, acc_stride;
   int has_res;
+  // pair mode (taps mode, wide N tiles): 2-CTA clusters; tcgen05.mma.cta_group::2 with M = 256 (each CTA's 128 pixels)
+  // and each CTA holding only HALF of the B stage -- operand bytes into each SM per MAC drop by a third
+  int pair;
+  int b_row0[kMaxNTiles];    // first row of each N tile's blocks in the 2-D weight tensor map
   // variants (taps mode): work items are (M tile, N tile, variant); a variant has its own tap list and its own output
   // tensor map -- the 4 sub-pixel phases of a transposed conv run as ONE launch, neighbouring CTAs working on the phases
   // of the same input tile at the same time, so the input comes from HBM once (the other phases hit L2)
@@ -167,10 +171,11 @@ __device__ __forceinline__ void epi_half(const uint32_t (&v)[32], const float* _
 
 struct OutMaps { CUtensorMap m[4]; };   // output tensor map per variant
 
-template <typename T, bool kDw, bool kRes>
+template <typename T, bool kDw, bool kRes, bool kPair>
 __global__ void __launch_bounds__(kDw ? kBaseThreads + kMathThreads : kBaseThreads, 1)
 fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ CUtensorMap tmap_in,
-                  const __grid_constant__ OutMaps tmaps_out, const __grid_constant__ CUtensorMap tmap_res) {
+                  const __grid_constant__ OutMaps tmaps_out, const __grid_constant__ CUtensorMap tmap_res,
+                  const __grid_constant__ CUtensorMap tmap_w) {
   extern __shared__ uint8_t smem_raw[];
   const ConvParams& p = a.p;
   const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -194,7 +199,12 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 * kMaxStages + 4 + kMaxRing);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = a.m_tiles * a.nt.nt * a.nvar;
+  // pair mode: the cluster (not the CTA) walks the item list; an item covers M tiles 2m and 2m+1 (one per CTA of the pair)
+  uint32_t crank = 0;
+  if constexpr (kPair) crank = cluster_ctarank();
+  const int total_tiles = (kPair ? a.m_tiles >> 1 : a.m_tiles) * a.nt.nt * a.nvar;
+  const int first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   // work item -> (M tile, N tile, variant), variant fastest
   auto split = [&](int item, int& mt, int& ntile, int& var) {
     int q = item;
@@ -202,6 +212,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
     if (a.nvar > 1) { q = item >> 2; var = item & 3; }     // nvar is 1 or 4
     mt = (int)fdiv((uint32_t)q, a.d_nt);
     ntile = q - mt * a.nt.nt;
+    if (kPair) mt = 2 * mt + (int)crank;
   };
 
   for (int i = threadIdx.x; i < kMaxC; i += blockDim.x) {
@@ -217,16 +228,20 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
       mbar_init(bar_hfull + 8u * s, 1);
       mbar_init(bar_hempty + 8u * s, kGroupWarps);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, kEpiThreads / 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, (kPair ? 2 : 1) * kEpiThreads / 32); }
     for (int i = 0; i < kMaxRing; ++i) mbar_init(bar_rfull + 8u * i, 1);
     fence_barrier_init();
     prefetch_tmap(&tmap_in);
     for (int v = 0; v < a.nvar; ++v) prefetch_tmap(&tmaps_out.m[v]);
     if (kRes) prefetch_tmap(&tmap_res);
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
+  if (warp == 4) {
+    if constexpr (kPair) tmem_alloc_2sm(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
+    else tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();      // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -235,7 +250,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
     if (lane == 0) {
       const char* wbase = reinterpret_cast<const char*>(p.w16);
       Ring ra(0, SA), rb(0, SB), rh(0, kDw ? SH : 1);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first; tile < total_tiles; tile += step) {
         int mt, ntile, var;
         split(tile, mt, ntile, var);
         const int ntaps = a.v_ntaps[var];
@@ -258,7 +273,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
           }
         } else {
           const int xb = x0 * p.istride, yb = y0 * p.istride;
-          if (a.b_res && tile == (int)blockIdx.x) {   // first tile of this CTA: bring in every weight block, once
+          if (a.b_res && tile == first) {   // first tile of this CTA: bring in every weight block, once
             mbar_arrive_expect_tx(bar_bfull, bytes * (uint32_t)(ntaps * a.nchunks));
             for (int t = 0; t < ntaps; ++t)
               for (int c = 0; c < a.nchunks; ++c)
@@ -270,9 +285,19 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
             for (int c = 0; c < a.nchunks; ++c) {
               mbar_wait(bar_aempty + 8u * ra.idx, ra.phase ^ 1u);
               const uint32_t bar = bar_afull + 8u * ra.idx;
-              mbar_arrive_expect_tx(bar, (a.b_res ? 0u : bytes) + (uint32_t)kAStageBytes);
-              tma_load_4d(sA + (uint32_t)ra.idx * kAStageBytes, &tmap_in, c * kBK, xt, yt, n_img, bar);
-              if (!a.b_res) bulk_g2s(sB + (uint32_t)ra.idx * a.b_stage_bytes, wsrc, bytes, bar);
+              if constexpr (kPair) {
+                // both CTAs' copies complete on the LEADER's full barrier; each CTA brings its own A tile and its half of B's rows
+                // (the weight box always has maxrows/2 rows; for a narrower last N tile the surplus rows are never read)
+                if (crank == 0) mbar_arrive_expect_tx(bar, 2u * ((uint32_t)(a.nt.maxrows >> 1) * 128u + (uint32_t)kAStageBytes));
+                tma_load_4d_2sm(sA + (uint32_t)ra.idx * kAStageBytes, &tmap_in, c * kBK, xt, yt, n_img, bar);
+                const int half = a.nt.rows[ntile] >> 1;
+                tma_load_2d_2sm(sB + (uint32_t)ra.idx * a.b_stage_bytes, &tmap_w, 0,
+                                (a.b_row0[ntile] + (a.v_wrow[var][t] * a.nchunks + c) * a.nt.rows[ntile] + (int)crank * half) >> 2, bar);
+              } else {
+                mbar_arrive_expect_tx(bar, (a.b_res ? 0u : bytes) + (uint32_t)kAStageBytes);
+                tma_load_4d(sA + (uint32_t)ra.idx * kAStageBytes, &tmap_in, c * kBK, xt, yt, n_img, bar);
+                if (!a.b_res) bulk_g2s(sB + (uint32_t)ra.idx * a.b_stage_bytes, wsrc, bytes, bar);
+              }
               wsrc += bytes;
               ra.advance(1);
             }
@@ -284,15 +309,18 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
     // ===================== MMA issuer =====================
     Ring ra(0, SA), rb(0, SB);
     int tcount = 0;
+    const bool issuer = !kPair || crank == 0;   // pair mode: the leader CTA issues the M = 256 MMAs for both
     const int last_ksteps = (p.Cin - (a.nchunks - 1) * kBK + 15) >> 4;   // K=16 steps of the last (possibly partial) chunk
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    for (int tile = first; tile < total_tiles; tile += step, ++tcount) {
       int mt_unused, ntile, var;
       split(tile, mt_unused, ntile, var);
       const int kblocks = a.v_ntaps[var] * a.nchunks;
       const uint32_t n = (uint32_t)a.nt.rows[ntile];
       // instruction descriptor: D = F32 (bits 4-5), A/B format (bits 7-9 / 10-12), K-major A and B, N>>3 at 17-22, M>>4 at 24-28
-      const uint32_t idesc = (1u << 4) | (Cv<T>::kFmt << 7) | (Cv<T>::kFmt << 10) | ((n >> 3) << 17) | ((kBM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (Cv<T>::kFmt << 7) | (Cv<T>::kFmt << 10) | ((n >> 3) << 17) |
+                             (((kPair ? 2 * kBM : kBM) >> 4) << 24);
       const int acc = tcount & 1;
+      if (!issuer) continue;
       mbar_wait(bar_tempty + 8u * acc, (uint32_t)(((tcount >> 1) & 1) ^ 1));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.acc_stride);
@@ -307,11 +335,18 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
           const int ksteps = (c == a.nchunks - 1) ? last_ksteps : 4;
           const uint64_t adesc = make_sdesc(sA + (uint32_t)sa * kAStageBytes);
           const uint64_t bdesc = make_sdesc(sB + (uint32_t)sb * a.b_stage_bytes);
-          for (int ks = 0; ks < ksteps; ++ks)  // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
-            umma_f16(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
-          umma_commit(bar_aempty + 8u * sa);                         // frees the stage(s) when these MMAs retire
-          if (kDw) umma_commit(bar_bempty + 8u * sb);
-          if (kb == kblocks - 1) umma_commit(bar_tfull + 8u * acc);  // accumulator complete
+          if constexpr (kPair) {
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_f16_2sm(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
+            umma_commit_2sm(bar_aempty + 8u * sa, (uint16_t)3);                         // frees the stage in BOTH CTAs
+            if (kb == kblocks - 1) umma_commit_2sm(bar_tfull + 8u * acc, (uint16_t)3);  // both epilogues
+          } else {
+            for (int ks = 0; ks < ksteps; ++ks)  // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
+              umma_f16(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
+            umma_commit(bar_aempty + 8u * sa);                         // frees the stage(s) when these MMAs retire
+            if (kDw) umma_commit(bar_bempty + 8u * sb);
+            if (kb == kblocks - 1) umma_commit(bar_tfull + 8u * acc);  // accumulator complete
+          }
         }
         __syncwarp();
         ra.advance(1);
@@ -325,7 +360,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
     const uint32_t row_off = (uint32_t)tid * 128u;
     const int rsw = tid & 7;
     // residual prefetch cursor (thread 0): slab sequence number -> (tile, slab)
-    int pf_tile = blockIdx.x, pf_slab = 0, pf_buf = 0;
+    int pf_tile = first, pf_slab = 0, pf_buf = 0;
     auto prefetch_res = [&]() {
       if (pf_tile < total_tiles) {
         int mt, ntile, var;
@@ -334,7 +369,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
         tile_coords(a, mt, n_img, y0, x0);
         mbar_arrive_expect_tx(bar_rfull + 8u * pf_buf, kSlabBytes);
         tma_load_4d(sO + (uint32_t)pf_buf * kSlabBytes, &tmap_res, a.nt.n0[ntile] + pf_slab * 64, x0, y0, n_img, bar_rfull + 8u * pf_buf);
-        if (++pf_slab * 64 >= a.nt.rows[ntile]) { pf_slab = 0; pf_tile += gridDim.x; }
+        if (++pf_slab * 64 >= a.nt.rows[ntile]) { pf_slab = 0; pf_tile += step; }
       }
       if (++pf_buf == R) pf_buf = 0;
     };
@@ -342,7 +377,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
       for (int i = 0; i < R - 1; ++i) prefetch_res();
     int tcount = 0;
     Ring rq(0, R);                           // output staging slab
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    for (int tile = first; tile < total_tiles; tile += step, ++tcount) {
       int mt, ntile, var;
       split(tile, mt, ntile, var);
       const int n0 = a.nt.n0[ntile], n = a.nt.rows[ntile];
@@ -367,7 +402,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
             if (j == nslabs - 1 && (h == 1 || c0 + 32 >= n)) {  // last read of this accumulator: hand it back to the MMA warp
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(bar_tempty + 8u * acc);
+              if (lane == 0) { if constexpr (kPair) mbar_arrive_leader(bar_tempty + 8u * acc); else mbar_arrive(bar_tempty + 8u * acc); }
             }
             if (p.relu6) epi_half<T, kRes, true>(v, s_scale + n0 + c0, s_shift + n0 + c0, srow, h, rsw);
             else epi_half<T, kRes, false>(v, s_scale + n0 + c0, s_shift + n0 + c0, srow, h, rsw);
@@ -401,7 +436,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
     const uint32_t h_thread = (uint32_t)col * (kBK * 2) + (uint32_t)cq * 8;
     float2 w[9][2];
     int cur_c = -1;
-    const int items = ((total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * a.nchunks;   // this CTA's (tile, chunk) items
+    const int items = ((total_tiles - first + step - 1) / step) * a.nchunks;   // this CTA's (tile, chunk) items
     Ring rh(grp, SH), ra(grp, SA);
     int c = grp % a.nchunks;
     for (int it = grp; it < items; it += 2) {
@@ -457,9 +492,11 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
   // teardown: everyone done with TMEM, then the allocating warp frees it
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();      // neither CTA retires while the other may still signal its barriers or read its smem
   if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+    if constexpr (kPair) tmem_dealloc_2sm(tmem_base, (uint32_t)a.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
   }
 }
 
@@ -468,24 +505,39 @@ size_t fused_smem_bytes(const FusedArgs& a) {
          (size_t)a.SH * kHaloBytes + 2 * kMaxC * sizeof(float) + (6 * kMaxStages + 4 + kMaxRing) * 8 + 16;
 }
 
-template <typename T, bool kDw, bool kRes>
-cudaError_t launch_t(const FusedArgs& a, const CUtensorMap& tin, const OutMaps& tout, const CUtensorMap& tres, int grid,
-                     size_t smem, cudaStream_t s) {
+template <typename T, bool kDw, bool kRes, bool kPair>
+cudaError_t launch_t(const FusedArgs& a, const CUtensorMap& tin, const OutMaps& tout, const CUtensorMap& tres, const CUtensorMap& tw,
+                     int grid, size_t smem, cudaStream_t s) {
   static thread_local int attr_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (attr_dev != dev) {
-    cudaError_t r = cudaFuncSetAttribute(fused_conv_kernel<T, kDw, kRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaError_t r = cudaFuncSetAttribute(fused_conv_kernel<T, kDw, kRes, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (r != cudaSuccess) return r;
     attr_dev = dev;
   }
-  fused_conv_kernel<T, kDw, kRes><<<grid, kDw ? kBaseThreads + kMathThreads : kBaseThreads, smem, s>>>(a, tin, tout, tres);
+  const int block = kDw ? kBaseThreads + kMathThreads : kBaseThreads;
+  if (kPair) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, fused_conv_kernel<T, kDw, kRes, kPair>, a, tin, tout, tres, tw);
+  }
+  fused_conv_kernel<T, kDw, kRes, kPair><<<grid, block, smem, s>>>(a, tin, tout, tres, tw);
   return cudaGetLastError();
 }
 
 }  // namespace
 
 static bool g_use_fused = true;
+static bool g_use_pair = true;
+void fused_set_pair(bool on) { g_use_pair = on; }
 void fused_set_enabled(bool on) { g_use_fused = on; }
 
 // dw != nullptr: the GEMM's A operand is the depthwise 3x3 (stride 1, rate 1, SAME) of p.in with weights dw [9][Cin]
@@ -573,6 +625,13 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
       return cudaErrorInvalidValue;
     }
   } else {
+    // CTA pairs for wide N tiles (the GEMM is bound by operand bytes into the SM): half a B stage per CTA
+    const int items_pair = (a.m_tiles >> 1) * a.nt.nt * nvar;
+    // (measured: a gain for the 1x1 GEMMs of the 728-wide trunk, a loss for the multi-tap dilated / transposed convs)
+    a.pair = (g_use_pair && nvar == 1 && p.ntaps == 1 && a.nt.maxrows >= 192 && !(a.m_tiles & 1) && items_pair >= num_sms) ? 1 : 0;
+    for (int i = 0; i < a.nt.nt && a.pair; ++i)
+      if (a.nt.rows[i] & 31) a.pair = 0;                   // N and N/2 stay multiples of 16
+    if (a.pair) a.b_stage_bytes = (((a.nt.maxrows >> 1) * 128) + 1023) & ~1023;
     a.SA = kMaxStages; a.SH = 0;
     a.SB = a.SA;
     while (fused_smem_bytes(a) > (size_t)kSmemLimit) {
@@ -583,7 +642,7 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
     // resident weights: when every B block of the launch fits next to >= 3 A stages, load them once per CTA instead of
     // once per tile -- the per-tile traffic into the SM drops to the A tiles alone
     const int nblocks = p.ntaps * a.nchunks;
-    if (a.nt.nt == 1 && nvar == 1 && nblocks <= 24) {
+    if (a.nt.nt == 1 && nvar == 1 && !a.pair && nblocks <= 24) {
       FusedArgs b = a;
       b.b_res = 1; b.SB = nblocks; b.SA = kMaxStages; b.ring = kMaxRing;
       while (fused_smem_bytes(b) > (size_t)kSmemLimit && (b.SA > 3 || b.ring > 2)) {
@@ -593,8 +652,14 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
     }
   }
   const bool bf16 = et == ET_BF16;
-  CUtensorMap tin, tres;
+  CUtensorMap tin, tres, tw;
   OutMaps tout;
+  memset(&tw, 0, sizeof tw);
+  if (a.pair) {
+    size_t rows_total = 0;
+    for (int i = 0; i < a.nt.nt; ++i) { a.b_row0[i] = (int)rows_total; rows_total += (size_t)a.nt.rows[i] * a.w_kblocks; }
+    if (!tma_encode_linear512(&tw, bf16, p.w16, rows_total * 128, (a.nt.maxrows >> 1) * 128)) return cudaErrorInvalidValue;
+  }
   memset(&tres, 0, sizeof tres);
   memset(&tout, 0, sizeof tout);
   void* in_base = reinterpret_cast<char*>(p.in.ptr) + (size_t)p.in.coff * 2;
@@ -622,12 +687,18 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
   const size_t smem = fused_smem_bytes(a);
   const int total_tiles = a.m_tiles * a.nt.nt * nvar;
   int grid = total_tiles < num_sms ? total_tiles : num_sms;
-  if (nvar == 4 && !(grid & 3)) --grid;   // a CTA strides the item list by the grid size: keep it odd so every CTA sees all 4 phases (8/4/4/2 k-blocks)
+  if (a.pair) {                          // clusters of 2 walk the pair-item list; an odd cluster count keeps the 4 phases balanced
+    int ncl = num_sms >> 1;
+    if (nvar == 4 && !(ncl & 1)) --ncl;
+    grid = 2 * ncl;
+  } else if (nvar == 4 && !(grid & 3)) --grid;   // a CTA strides the item list by the grid size: keep it odd so every CTA sees all 4 phases (8/4/4/2 k-blocks)
 #define EMD_DISPATCH(TT)                                                                                                   \
-  (a.dw_mode ? (a.has_res ? launch_t<TT, true, true>(a, tin, tout, tres, grid, smem, s)                                    \
-                          : launch_t<TT, true, false>(a, tin, tout, tres, grid, smem, s))                                  \
-             : (a.has_res ? launch_t<TT, false, true>(a, tin, tout, tres, grid, smem, s)                                   \
-                          : launch_t<TT, false, false>(a, tin, tout, tres, grid, smem, s)))
+  (a.dw_mode ? (a.has_res ? launch_t<TT, true, true, false>(a, tin, tout, tres, tw, grid, smem, s)                         \
+                          : launch_t<TT, true, false, false>(a, tin, tout, tres, tw, grid, smem, s))                       \
+   : a.pair  ? (a.has_res ? launch_t<TT, false, true, true>(a, tin, tout, tres, tw, grid, smem, s)                         \
+                          : launch_t<TT, false, false, true>(a, tin, tout, tres, tw, grid, smem, s))                       \
+             : (a.has_res ? launch_t<TT, false, true, false>(a, tin, tout, tres, tw, grid, smem, s)                        \
+                          : launch_t<TT, false, false, false>(a, tin, tout, tres, tw, grid, smem, s)))
   if (bf16) return EMD_DISPATCH(__nv_bfloat16);
   return EMD_DISPATCH(__half);
 #undef EMD_DISPATCH

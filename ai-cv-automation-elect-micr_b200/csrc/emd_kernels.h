@@ -126,6 +126,7 @@ cudaError_t launch_conv_fused(const ConvParams& p, int et, const float* dw, int 
 bool fused_multi_supported(const ConvParams* ps, int nvar, int et);
 cudaError_t launch_conv_fused_multi(const ConvParams* ps, int nvar, int et, int num_sms, cudaStream_t s);
 void fused_set_enabled(bool on);
+void fused_set_pair(bool on);    // 2-CTA (cta_group::2) GEMM for wide N tiles; default on
 
 // emd_kernels_wrap.cu: whole-image wrapper kernels
 cudaError_t launch_minmax(const void* img, int in_f64, size_t n, double* d_minmax /*[2]*/, void* d_partial,
