@@ -156,7 +156,7 @@ struct Builder {
   }
 };
 
-void build_schedule_A(emd_engine* e) {
+void build_schedule(emd_engine* e) {
   Builder b{e};
   const int S = e->S, f0 = 64, f1 = 128, f2 = 256, f3 = 728, f4 = 728, ao = 256;
   e->t_input = b.add_tensor("input", S, S, 1, true);
@@ -201,14 +201,18 @@ void build_schedule_A(emd_engine* e) {
     b.sep(base + "2", b.whole(t1), b.whole(t2), f4, f4, 1, 1, trunk);
     trunk = b.whole(t2);
   }
-  // ASPP (DMG:291-361): branches write straight into their slice of the 3640-channel concat
+  // ASPP: branches write straight into their slice of the 3640-channel concat
   b.conv("aspp_1x1", trunk, b.slice(cat5, 0, f4, "aspp_1x1"), f4, f4, 1, 1, 1, true);
   const int rates[3] = {6, 12, 18};
-  for (int i = 0; i < 3; ++i) {
-    const std::string n = "aspp_r" + std::to_string(rates[i]);
-    b.conv(n, trunk, b.slice(cat5, (i + 1) * f4, f4, n), f4, f4, 3, 1, rates[i], true);
-  }
-  {
+  auto bn_relu6 = [&](const std::string& name, Ref in, Ref out, int C) {   // stand-alone BatchNorm + ReLU6 = identity "resize" with an affine
+    Step r; r.kind = SK_RESIZE; r.name = name; r.layer = name; r.in = in; r.out = out; r.Cin = r.Cout = C; r.relu6 = true; r.wname = name;
+    e->steps.push_back(r);
+  };
+  if (e->variant == EMD_VARIANT_A) {   // DMG:291-361: dense dilated 3x3 branches; avg-pool -> 1x1 conv -> resize -> BN -> ReLU6
+    for (int i = 0; i < 3; ++i) {
+      const std::string n = "aspp_r" + std::to_string(rates[i]);
+      b.conv(n, trunk, b.slice(cat5, (i + 1) * f4, f4, n), f4, f4, 3, 1, rates[i], true);
+    }
     int tp = b.add_tensor("aspp_pool", s16 / 2, s16 / 2, f4);
     int ti = b.add_tensor("aspp_image_conv", s16 / 2, s16 / 2, f4);
     Step p; p.kind = SK_POOL; p.name = "aspp_pool"; p.layer = "aspp_image"; p.in = trunk; p.out = b.whole(tp);
@@ -219,6 +223,15 @@ void build_schedule_A(emd_engine* e) {
     Step r; r.kind = SK_RESIZE; r.name = "aspp_image"; r.layer = "aspp_image"; r.in = b.whole(ti);
     r.out = b.slice(cat5, 4 * f4, f4, "aspp_image"); r.Cin = r.Cout = f4; r.relu6 = true; r.wname = "aspp_image:post";
     e->steps.push_back(r);
+  } else {   // DEN:152-218: separable dilated branches (BN, BN, ReLU6) each followed by another BN -> ReLU6; the image-level
+             // branch is resize_images(input, [32,32]) = identity -> BN -> ReLU6 (the pooled tensor is computed and discarded, DEN:185-200)
+    for (int i = 0; i < 3; ++i) {
+      const std::string n = "aspp_r" + std::to_string(rates[i]);
+      int tb = b.add_tensor(n, s16, s16, f4);
+      b.sep(n, trunk, b.whole(tb), f4, f4, 1, rates[i]);
+      bn_relu6(n + "_post", b.whole(tb), b.slice(cat5, (i + 1) * f4, f4, n + "_post"), f4);
+    }
+    bn_relu6("aspp_image", trunk, b.slice(cat5, 4 * f4, f4, "aspp_image"), f4);
   }
   int taspp = b.add_tensor("aspp_pellet", s16, s16, ao);
   b.conv("aspp_pellet", b.whole(cat5), b.whole(taspp), 5 * f4, ao, 1, 1, 1, true);
@@ -248,7 +261,8 @@ void build_schedule_A(emd_engine* e) {
   b.conv("residual0_d", b.whole(d1to0), b.whole(d0r), f1, f0, 1, 1, 1, true);
   b.sep("deconv0_1", b.whole(d0a), b.whole(dec0), f0, f0, 1, 1, b.whole(d0r));
   // final 3x3 conv -> BN -> ReLU6 (DMG:531) + in-graph clip (DMG:534-538), written as f32
-  b.conv("final", b.whole(dec0), b.whole(e->t_output), f0, 1, 3, 1, 1, true, Ref(), true);
+  // variant A clips in-graph (DMG:534-538); variant B returns the raw prediction (DEN:390-396), the wrapper clips (DEN:648-649)
+  b.conv("final", b.whole(dec0), b.whole(e->t_output), f0, 1, 3, 1, 1, true, Ref(), e->variant == EMD_VARIANT_A);
 }
 
 // algorithmic work per crop of each step (16-bit storage), for roofline reporting
@@ -405,9 +419,14 @@ int bind_weights(emd_engine* e, const char* host_blob) {
       }
       case SK_RESIZE:
         if (s.wname.empty()) break;
-        if (!(s.scale = entry_ptr(e, "aspp_image/scale", 1, s.Cout, &why)) ||
-            !(s.shift = entry_ptr(e, "aspp_image/bnshift", 1, s.Cout, &why)))
+        if (s.wname == "aspp_image:post") {   // variant A: BN after the resized image-level conv (DMG:345)
+          if (!(s.scale = entry_ptr(e, "aspp_image/scale", 1, s.Cout, &why)) ||
+              !(s.shift = entry_ptr(e, "aspp_image/bnshift", 1, s.Cout, &why)))
+            return fail(e, EMD_EINVAL, "%s", why.c_str());
+        } else if (!(s.scale = entry_ptr(e, s.wname + "/scale", 1, s.Cout, &why)) ||
+                   !(s.shift = entry_ptr(e, s.wname + "/shift", 1, s.Cout, &why))) {
           return fail(e, EMD_EINVAL, "%s", why.c_str());
+        }
         break;
       default: break;
     }
@@ -661,7 +680,7 @@ int emd_create(emd_engine** out, int device, int cropsize, int variant, int max_
   if (!out) return fail(nullptr, EMD_EINVAL, "out is NULL");
   *out = nullptr;
   if (cropsize < 32 || cropsize % 32) return fail(nullptr, EMD_EINVAL, "cropsize %d: must be a multiple of 32 (>= 32)", cropsize);
-  if (variant != EMD_VARIANT_A) return fail(nullptr, EMD_EINVAL, "variant %d not built (only EMD_VARIANT_A)", variant);
+  if (variant != EMD_VARIANT_A && variant != EMD_VARIANT_B) return fail(nullptr, EMD_EINVAL, "variant %d (EMD_VARIANT_A or EMD_VARIANT_B)", variant);
   if (max_batch < 1) return fail(nullptr, EMD_EINVAL, "max_batch %d", max_batch);
   int ndev = 0;
   cudaError_t r = cudaGetDeviceCount(&ndev);
@@ -698,7 +717,7 @@ int emd_create(emd_engine** out, int device, int cropsize, int variant, int max_
   }
   e->num_sms = prop.multiProcessorCount;
   CUC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  build_schedule_A(e);
+  build_schedule(e);
   annotate_work(e);
   int rc = plan_arena(e);
   if (rc != EMD_OK) { g_create_error = e->err; emd_destroy(e); return rc; }

@@ -62,20 +62,23 @@ class Denoiser(object):
     visible_cuda: like the reference, a string put into CUDA_VISIBLE_DEVICES (DEN:591); None leaves
         the environment alone (the reference raises TypeError there, App. D).
     Extra keyword arguments (not in the reference): device, mode ('bf16' | 'fp16' | 'fp32'),
-        cropsize (multiple of 32), max_batch.
+        cropsize (multiple of 32), max_batch, variant ('A' = misc_py/denoiser-multi-gpu.py:200-540, the canonical
+        dense-ASPP graph with the in-graph clip; 'B' = machine_learning/denoiser.py:58-398, the graph of the deployed
+        class file: separable ASPP branches with an extra BN/ReLU6, identity image branch, clip in the wrapper).
     """
 
     def __init__(self, checkpoint_loc=None, visible_cuda=None, *, device=0, mode="bf16", cropsize=CROPSIZE,
-                 max_batch=32, seed=0):
+                 max_batch=32, seed=0, variant="A"):
         if visible_cuda is not None:
             os.environ["CUDA_VISIBLE_DEVICES"] = visible_cuda
         self.cropsize = cropsize
         self.mode = mode
-        self.engine = Engine(device=device, cropsize=cropsize, max_batch=max_batch)
+        self.variant = variant
+        self.engine = Engine(device=device, cropsize=cropsize, max_batch=max_batch, variant=variant)
         if checkpoint_loc is None:
-            blob = _weights.pack(_weights.init_reference_weights(seed))
+            blob = _weights.pack(_weights.init_reference_weights(seed, variant), variant)
         elif isinstance(checkpoint_loc, dict):
-            blob = _weights.pack(checkpoint_loc)
+            blob = _weights.pack(checkpoint_loc, variant)
         elif isinstance(checkpoint_loc, (bytes, bytearray)):
             blob = bytes(checkpoint_loc)
         else:

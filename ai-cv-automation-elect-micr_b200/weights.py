@@ -31,9 +31,10 @@ NUM_EXTRA_BLOCKS = 11                  # DMG:63
 
 
 def layer_table(variant: str = "A"):
-    """[(name, kind, cin, cout, k)] in the graph's creation order (DMG:392-531)."""
-    if variant != "A":
-        raise NotImplementedError("only variant A (misc_py/denoiser-multi-gpu.py) is built")
+    """[(name, kind, cin, cout, k)] in the graph's creation order (variant A: DMG:392-531; variant B: DEN:250-389).
+    kind 'bn' = a stand-alone BatchNorm + ReLU6 (variant B only, DEN:166-200)."""
+    if variant not in ("A", "B"):
+        raise ValueError(f"unknown graph variant {variant!r}")
     f0, f1, f2, f3, f4 = FEATURES
     t = []
     for i, (cin, a, b, c) in enumerate([(1, f0, f0, f1), (f1, f1, f1, f1), (f1, f2, f2, f2), (f2, f3, f3, f3)]):
@@ -43,8 +44,14 @@ def layer_table(variant: str = "A"):
     for blk in range(NUM_EXTRA_BLOCKS):
         t += [(f"mid{blk}_{j}", "sep", f4, f4, 3) for j in range(3)]
     t += [("aspp_1x1", "conv", f4, f4, 1)]
-    t += [(f"aspp_r{r}", "conv", f4, f4, 3) for r in ASPP_RATES]
-    t += [("aspp_image", "conv", f4, f4, 1), ("aspp_pellet", "conv", 5 * f4, ASPP_OUTPUT, 1)]
+    if variant == "A":   # dense dilated branches + pooled image-level conv (DMG:306-345)
+        t += [(f"aspp_r{r}", "conv", f4, f4, 3) for r in ASPP_RATES]
+        t += [("aspp_image", "conv", f4, f4, 1)]
+    else:                # separable dilated branches each followed by another BN + ReLU6; identity image branch (DEN:166-200)
+        for r in ASPP_RATES:
+            t += [(f"aspp_r{r}", "sep", f4, f4, 3), (f"aspp_r{r}_post", "bn", f4, f4, 0)]
+        t += [("aspp_image", "bn", f4, f4, 0)]
+    t += [("aspp_pellet", "conv", 5 * f4, ASPP_OUTPUT, 1)]
     t += [("deconv2_0", "sep", ASPP_OUTPUT + f1, f2, 3), ("deconv2_1", "sep", f2, f2, 3),
           ("residual2_d", "conv", ASPP_OUTPUT + f1, f2, 1), ("deconv2to1", "deconv", f2, f2, 3),
           ("deconv1_0", "sep", f2 + f1, f1, 3), ("deconv1_1", "sep", f1, f1, 3),
@@ -82,6 +89,8 @@ def init_reference_weights(seed: int = 0, variant: str = "A"):
             p[f"{name}/kernel"] = glorot((k, k, cin, cout))
             p[f"{name}/bias"] = np.zeros(cout, np.float32)
             bn(f"{name}/bn", cout)
+        elif kind == "bn":
+            bn(f"{name}/bn", cout)
         else:
             p[f"{name}/tkernel"] = glorot((3, 3, cout, cin))
             p[f"{name}/bias"] = np.zeros(cout, np.float32)
@@ -107,6 +116,8 @@ def fold(params, variant: str = "A"):
             a1, b1 = _bn_affine(params, f"{name}/bn1")
             a2, b2 = _bn_affine(params, f"{name}/bn2")
             scale, shift = a1 * a2, a2 * b1 + b2          # bn2(bn1(x))
+        elif kind == "bn":
+            scale, shift = _bn_affine(params, f"{name}/bn")
         else:
             if kind == "conv":
                 w = params[f"{name}/kernel"].reshape(k * k * cin, cout)
@@ -115,7 +126,7 @@ def fold(params, variant: str = "A"):
             out[f"{name}/w"] = w
             a, b = _bn_affine(params, f"{name}/bn")
             bias = params[f"{name}/bias"].astype(np.float64)
-            if name == "aspp_image":
+            if name == "aspp_image" and variant == "A":
                 # conv + bias, THEN resize, THEN BN/ReLU6 (DMG:338-345): keep them apart
                 out["aspp_image/one"] = np.ones((1, cout))
                 out["aspp_image/bias"] = bias.reshape(1, cout)

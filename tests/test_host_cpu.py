@@ -139,3 +139,17 @@ def test_scale0to1_dropin(emd):
     assert out.dtype == np.float32 and out.tolist() == [[0.0, 0.5], [0.25, 1.0]]
     c = np.full((2, 2), 3.0)
     assert (emd.scale0to1(c) == 0.5).all() and (c == 0.5).all()  # in-place fill like DEN:690-691
+
+
+def test_weight_exporter_covers_both_graph_variants():
+    """layer tables match the oracle's creation-order inventories; a packed variant-B blob carries the stand-alone BN layers."""
+    import importlib
+    from oracle.net import layer_specs
+    w = importlib.import_module("ai-cv-automation-elect-micr_b200.weights")
+    for v in "AB":
+        assert [tuple(t) for t in w.layer_table(v)] == [tuple(t) for t in layer_specs(v)]
+    f = w.fold(w.init_reference_weights(0, "B"), "B")
+    assert f["aspp_r6_post/scale"].shape == (1, 728) and f["aspp_image/shift"].shape == (1, 728) and "aspp_image/bias" not in f
+    assert f["aspp_r12/dw"].shape == (9, 728) and f["aspp_r12/w"].shape == (728, 728)
+    blob = w.pack(w.init_reference_weights(0, "B"), "B")
+    assert blob[:8] == b"EMDW0001" and int.from_bytes(blob[12:16], "little") == 1
