@@ -20,6 +20,7 @@
 #include "emd_kernels.h"
 #include "emd_tma.h"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace emd {
@@ -311,6 +312,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
     int tcount = 0;
     const bool issuer = !kPair || crank == 0;   // pair mode: the leader CTA issues the M = 256 MMAs for both
     const int last_ksteps = (p.Cin - (a.nchunks - 1) * kBK + 15) >> 4;   // K=16 steps of the last (possibly partial) chunk
+    const uint32_t a_lo0 = sdesc_lo(sA), b_lo0 = sdesc_lo(sB), b_step = (uint32_t)a.b_stage_bytes >> 4;   // descriptor low words of stage 0
     for (int tile = first; tile < total_tiles; tile += step, ++tcount) {
       int mt_unused, ntile, var;
       split(tile, mt_unused, ntile, var);
@@ -332,17 +334,16 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
         if (kDw) mbar_wait(bar_bfull + 8u * sb, rb.phase);
         tc_fence_after();
         if (lane == 0) {
-          const int ksteps = (c == a.nchunks - 1) ? last_ksteps : 4;
-          const uint64_t adesc = make_sdesc(sA + (uint32_t)sa * kAStageBytes);
-          const uint64_t bdesc = make_sdesc(sB + (uint32_t)sb * a.b_stage_bytes);
+          const uint32_t a_lo = a_lo0 + (uint32_t)sa * (kAStageBytes >> 4), b_lo = b_lo0 + (uint32_t)sb * b_step;
+          const uint32_t accum = kb != 0 ? 1u : 0u;
+          if (c != a.nchunks - 1 || last_ksteps == 4) umma_kblock<kPair, 4>(d_tmem, a_lo, b_lo, idesc, accum);
+          else if (last_ksteps == 3) umma_kblock<kPair, 3>(d_tmem, a_lo, b_lo, idesc, accum);
+          else if (last_ksteps == 2) umma_kblock<kPair, 2>(d_tmem, a_lo, b_lo, idesc, accum);
+          else umma_kblock<kPair, 1>(d_tmem, a_lo, b_lo, idesc, accum);
           if constexpr (kPair) {
-            for (int ks = 0; ks < ksteps; ++ks)
-              umma_f16_2sm(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
             umma_commit_2sm(bar_aempty + 8u * sa, (uint16_t)3);                         // frees the stage in BOTH CTAs
             if (kb == kblocks - 1) umma_commit_2sm(bar_tfull + 8u * acc, (uint16_t)3);  // both epilogues
           } else {
-            for (int ks = 0; ks < ksteps; ++ks)  // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
-              umma_f16(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
             umma_commit(bar_aempty + 8u * sa);                         // frees the stage(s) when these MMAs retire
             if (kDw) umma_commit(bar_bempty + 8u * sb);
             if (kb == kblocks - 1) umma_commit(bar_tfull + 8u * acc);  // accumulator complete
@@ -627,8 +628,8 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
   } else {
     // CTA pairs for wide N tiles (the GEMM is bound by operand bytes into the SM): half a B stage per CTA
     const int items_pair = (a.m_tiles >> 1) * a.nt.nt * nvar;
-    // (measured: a gain for the 1x1 GEMMs of the 728-wide trunk, a loss for the multi-tap dilated / transposed convs)
-    a.pair = (g_use_pair && nvar == 1 && p.ntaps == 1 && a.nt.maxrows >= 192 && !(a.m_tiles & 1) && items_pair >= num_sms) ? 1 : 0;
+    static const int pair_min_rows = getenv("EMD_PAIR_MIN_ROWS") ? atoi(getenv("EMD_PAIR_MIN_ROWS")) : 128;   // tuning switch
+    a.pair = (g_use_pair && a.nt.maxrows >= pair_min_rows && !(a.m_tiles & 1) && items_pair >= num_sms) ? 1 : 0;
     for (int i = 0; i < a.nt.nt && a.pair; ++i)
       if (a.nt.rows[i] & 31) a.pair = 0;                   // N and N/2 stay multiples of 16
     if (a.pair) a.b_stage_bytes = (((a.nt.maxrows >> 1) * 128) + 1023) & ~1023;

@@ -184,6 +184,64 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, ui
       "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// One K block (up to four K=16 steps) in a single PTX block: the descriptors' high words (SBO 1024 B, version 1,
+// SWIZZLE_128B) are constants, the low words advance by 2 (32 bytes >> 4) per step.  Keeping the address arithmetic out
+// of the issuing thread's instruction stream matters: one thread issues every MMA of the CTA, and a loop of a dozen
+// dependent instructions per tcgen05.mma makes the kernel issue-bound (measured ~250 cycles per MMA before).
+template <bool kPair, int kSteps>
+__device__ __forceinline__ void umma_kblock(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum_first) {
+  constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // bits 32-45 SBO, 46 version, 61-63 layout
+  static_assert(kSteps >= 1 && kSteps <= 4, "K block is at most 64 channels");
+#define EMD_MMA(G, STEP, PRED)                                                                                   \
+  "add.u32 al, %1, " #STEP ";\n\tadd.u32 bl, %2, " #STEP ";\n\tmov.b64 da, {al, %4};\n\tmov.b64 db, {bl, %4};\n\t" \
+  "tcgen05.mma.cta_group::" #G ".kind::f16 [%0], da, db, %3, " PRED ";\n\t"
+  if constexpr (!kPair) {
+    if constexpr (kSteps == 4)
+      asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\tsetp.ne.b32 p, %5, 0;\n\t" EMD_MMA(1, 0, "p")
+                       EMD_MMA(1, 2, "1") EMD_MMA(1, 4, "1") EMD_MMA(1, 6, "1") "}" ::"r"(d_tmem),
+                   "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(kHi), "r"(accum_first)
+                   : "memory");
+    else if constexpr (kSteps == 3)
+      asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\tsetp.ne.b32 p, %5, 0;\n\t" EMD_MMA(1, 0, "p")
+                       EMD_MMA(1, 2, "1") EMD_MMA(1, 4, "1") "}" ::"r"(d_tmem),
+                   "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(kHi), "r"(accum_first)
+                   : "memory");
+    else if constexpr (kSteps == 2)
+      asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\tsetp.ne.b32 p, %5, 0;\n\t" EMD_MMA(1, 0, "p")
+                       EMD_MMA(1, 2, "1") "}" ::"r"(d_tmem),
+                   "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(kHi), "r"(accum_first)
+                   : "memory");
+    else
+      asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\tsetp.ne.b32 p, %5, 0;\n\t" EMD_MMA(1, 0, "p") "}" ::"r"(
+                       d_tmem),
+                   "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(kHi), "r"(accum_first)
+                   : "memory");
+  } else {
+    if constexpr (kSteps == 4)
+      asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\tsetp.ne.b32 p, %5, 0;\n\t" EMD_MMA(2, 0, "p")
+                       EMD_MMA(2, 2, "1") EMD_MMA(2, 4, "1") EMD_MMA(2, 6, "1") "}" ::"r"(d_tmem),
+                   "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(kHi), "r"(accum_first)
+                   : "memory");
+    else if constexpr (kSteps == 3)
+      asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\tsetp.ne.b32 p, %5, 0;\n\t" EMD_MMA(2, 0, "p")
+                       EMD_MMA(2, 2, "1") EMD_MMA(2, 4, "1") "}" ::"r"(d_tmem),
+                   "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(kHi), "r"(accum_first)
+                   : "memory");
+    else if constexpr (kSteps == 2)
+      asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\tsetp.ne.b32 p, %5, 0;\n\t" EMD_MMA(2, 0, "p")
+                       EMD_MMA(2, 2, "1") "}" ::"r"(d_tmem),
+                   "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(kHi), "r"(accum_first)
+                   : "memory");
+    else
+      asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\tsetp.ne.b32 p, %5, 0;\n\t" EMD_MMA(2, 0, "p") "}" ::"r"(
+                       d_tmem),
+                   "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(kHi), "r"(accum_first)
+                   : "memory");
+  }
+#undef EMD_MMA
+}
+// low word of a K-major SWIZZLE_128B descriptor: start address >> 4 (14 bits) | LBO field = 1
+__device__ __forceinline__ uint32_t sdesc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 // D[tmem] (+)= A[smem] * B[smem], kind::f16 (BF16 or FP16 operands, FP32 accumulate)
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(

@@ -291,7 +291,7 @@ def main():
         roof["top_steps_ms"] = {i[0]: round(i[1], 3) for i in top}
         out["roofline"] = roof
         if not args.no_cpu_baseline:
-            n_pass = 3
+            n_pass = 12   # ~10 s of CPU work on the box's host cores
             v, cores = time_cpu_oracle(n_pass, S)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": f"median of {n_pass} batch-1 passes of the PyTorch-CPU oracle over one "
