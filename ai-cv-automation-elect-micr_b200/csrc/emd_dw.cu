@@ -155,6 +155,104 @@ __global__ void __launch_bounds__(kMathThreads + 32, 1) dw_tma_kernel(const __gr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// stride 2 (the DepthwiseConv2dNative of the cnnN_strided blocks, DMG:402/417/432/447; TF SAME on even sizes pads
+// 0 before / 1 after, so output (y, x) reads input rows 2y..2y+2, columns 2x..2x+2).  Item = 8 x 8 output pixels of a
+// 64-channel chunk; TMA brings the 17 x 17 input patch.  Four groups of four warps, group g owns pipeline stage g;
+// thread = 4 channels x 1 output column x 8 output rows, the bottom window row is carried to the next output row.
+// ---------------------------------------------------------------------------------------------
+constexpr int kS2T = 8, kS2Halo = 2 * kS2T + 1;
+constexpr int kS2StageBytes = kS2Halo * kS2Halo * kChunk * 2;   // 36992
+constexpr int kS2Groups = 4, kS2GroupThreads = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(kS2Groups* kS2GroupThreads + 32, 1) dw_s2_tma_kernel(const __grid_constant__ DwTmaArgs a,
+                                                                                       const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 127u) & ~127u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kS2Groups * kS2StageBytes);
+  const uint32_t bar_full = ptx::smem_u32(bars), bar_empty = bar_full + 8u * kS2Groups;
+  const DwParams& p = a.p;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kS2Groups; ++s) { ptx::mbar_init(bar_full + 8u * s, 1); ptx::mbar_init(bar_empty + 8u * s, kS2GroupThreads / 32); }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&tmap);
+  }
+  __syncthreads();
+  const int my_items = (a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (threadIdx.x >= kS2Groups * kS2GroupThreads) {
+    if (threadIdx.x == kS2Groups * kS2GroupThreads) {   // producer
+      for (int k = 0, item = blockIdx.x; k < my_items; ++k, item += gridDim.x) {
+        const int tile = item / a.nchunks, c = item - tile * a.nchunks;
+        const int n_img = tile / a.tiles_per_img;
+        const int rem = tile - n_img * a.tiles_per_img;
+        const int by = rem / a.tiles_x, bx = rem - by * a.tiles_x;
+        const int s = k % kS2Groups;
+        ptx::mbar_wait(bar_empty + 8u * s, (uint32_t)(((k / kS2Groups) & 1) ^ 1));
+        ptx::mbar_arrive_expect_tx(bar_full + 8u * s, kS2StageBytes);
+        ptx::tma_load_4d(base + (uint32_t)s * kS2StageBytes, &tmap, c * kChunk, 2 * bx * kS2T, 2 * by * kS2T, n_img, bar_full + 8u * s);
+      }
+    }
+    return;
+  }
+
+  const int grp = threadIdx.x >> 7, tg = threadIdx.x & 127, lane = threadIdx.x & 31;
+  const int cq = tg & 15, col = tg >> 4;      // 4-channel quad, output column 0..7
+  int cur_c = -1;
+  float2 w[9][2];
+  for (int k = grp; k < my_items; k += kS2Groups) {
+    const int item = blockIdx.x + k * gridDim.x;
+    const int tile = item / a.nchunks, c = item - tile * a.nchunks;
+    const int n_img = tile / a.tiles_per_img;
+    const int rem = tile - n_img * a.tiles_per_img;
+    const int by = rem / a.tiles_x, bx = rem - by * a.tiles_x;
+    const int ch = c * kChunk + cq * 4;
+    const bool ch_ok = ch < p.in.C;
+    if (c != cur_c) {
+      cur_c = c;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ch_ok) w0 = __ldg(reinterpret_cast<const float4*>(p.w + t * p.in.C + ch));
+        w[t][0] = make_float2(w0.x, w0.y); w[t][1] = make_float2(w0.z, w0.w);
+      }
+    }
+    ptx::mbar_wait(bar_full + 8u * grp, (uint32_t)((k / kS2Groups) & 1));
+    const uint8_t* hb = smem + (size_t)grp * kS2StageBytes + (2 * col) * (kChunk * 2) + cq * 8;
+    float2 win[3][3][2];
+    auto load_row = [&](int hy, float2 (&dst)[3][2]) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const uint2 u = *reinterpret_cast<const uint2*>(hb + (hy * kS2Halo + kx) * (kChunk * 2));
+        dst[kx][0] = Up<T>::up(u.x); dst[kx][1] = Up<T>::up(u.y);
+      }
+    };
+    load_row(0, win[0]);
+    const size_t opix = ((size_t)n_img * p.out.H + by * kS2T) * p.out.W + bx * kS2T + col;
+#pragma unroll
+    for (int i = 0; i < kS2T; ++i) {
+      // window rows for output row i: halo rows 2i, 2i+1, 2i+2 live in win[(2i)%3], win[(2i+1)%3], win[(2i+2)%3]
+      load_row(2 * i + 1, win[(2 * i + 1) % 3]);
+      load_row(2 * i + 2, win[(2 * i + 2) % 3]);
+      float2 acc0 = ptx::fmul2(win[(2 * i) % 3][0][0], w[0][0]), acc1 = ptx::fmul2(win[(2 * i) % 3][0][1], w[0][1]);
+#pragma unroll
+      for (int t = 1; t < 9; ++t) {
+        acc0 = ptx::ffma2(win[(2 * i + t / 3) % 3][t % 3][0], w[t][0], acc0);
+        acc1 = ptx::ffma2(win[(2 * i + t / 3) % 3][t % 3][1], w[t][1], acc1);
+      }
+      if (ch_ok) {
+        T* op = reinterpret_cast<T*>(p.out.ptr) + (opix + (size_t)i * p.out.W) * p.out.pitch + p.out.coff + ch;
+        *reinterpret_cast<uint2*>(op) = make_uint2(Up<T>::pack(acc0.x, acc0.y), Up<T>::pack(acc1.x, acc1.y));
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(bar_empty + 8u * grp);
+  }
+}
+
 }  // namespace
 
 bool dw_tma_supported(const DwParams& p, int et) {
@@ -200,6 +298,45 @@ cudaError_t launch_dw_tma(const DwParams& p, int et, int num_sms, cudaStream_t s
   DwTmaArgs a;
   a.p = p; a.scale = 1.f; a.shift = 0.f; a.relu6 = a.clip01 = 0;
   return launch_common(a, et, false, num_sms, s);
+}
+
+// stride 2, TF SAME on even input sizes (pad 0 before / 1 after)
+bool dw_s2_tma_supported(const DwParams& p, int et) {
+  if (et != ET_BF16 && et != ET_F16) return false;
+  if (p.in_f32 || p.stride != 2 || p.rate != 1 || p.pad != 0) return false;
+  if (p.OH % kS2T || p.OW % kS2T || p.in.H != 2 * p.OH || p.in.W != 2 * p.OW) return false;
+  if ((p.in.C & 7) || (p.in.pitch & 7) || (p.in.coff & 7) || (p.out.pitch & 7) || (p.out.coff & 7)) return false;
+  return tma_encoder() != nullptr;
+}
+
+template <typename T>
+static cudaError_t launch_s2_t(const DwTmaArgs& a, const CUtensorMap& tmap, int grid, size_t smem, cudaStream_t s) {
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr_dev != dev) {
+    cudaError_t r = cudaFuncSetAttribute(dw_s2_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (r != cudaSuccess) return r;
+    attr_dev = dev;
+  }
+  dw_s2_tma_kernel<T><<<grid, kS2Groups * kS2GroupThreads + 32, smem, s>>>(a, tmap);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dw_s2_tma(const DwParams& p, int et, int num_sms, cudaStream_t s) {
+  DwTmaArgs a;
+  a.p = p; a.scale = 1.f; a.shift = 0.f; a.relu6 = a.clip01 = 0;
+  a.tiles_x = p.OW / kS2T;
+  a.tiles_per_img = (p.OH / kS2T) * a.tiles_x;
+  a.nchunks = (p.in.C + kChunk - 1) / kChunk;
+  a.items = p.N * a.tiles_per_img * a.nchunks;
+  CUtensorMap tmap;
+  void* base = reinterpret_cast<char*>(p.in.ptr) + (size_t)p.in.coff * 2;
+  if (!tma_encode_nhwc(&tmap, et == ET_BF16, base, p.in.C, p.in.W, p.in.H, p.N, p.in.pitch, kChunk, kS2Halo, kS2Halo, 1, false))
+    return cudaErrorInvalidValue;
+  const size_t smem = 128 + (size_t)kS2Groups * kS2StageBytes + 2 * kS2Groups * 8;
+  const int grid = a.items < num_sms ? a.items : num_sms;
+  return et == ET_BF16 ? launch_s2_t<__nv_bfloat16>(a, tmap, grid, smem, s) : launch_s2_t<__half>(a, tmap, grid, smem, s);
 }
 
 // final 3x3 conv 64 -> 1 (conv_block_not_sep(deconv0, 1), DMG:531) + clip (DMG:534-538) as a channel-reducing

@@ -547,6 +547,7 @@ cudaError_t run_step_impl(ExecCtx& c, int idx) {
       p.w = s.dw; p.in_f32 = ti.external;
       e->launches++;
       if (e->use_umma && dw_tma_supported(p, c.et)) return launch_dw_tma(p, c.et, e->num_sms, c.s);
+      if (e->use_umma && dw_s2_tma_supported(p, c.et)) return launch_dw_s2_tma(p, c.et, e->num_sms, c.s);
       return launch_dw3x3(p, c.et, c.s);
     }
     case SK_POOL: {

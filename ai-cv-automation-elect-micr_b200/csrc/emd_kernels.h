@@ -86,6 +86,8 @@ cudaError_t launch_uncast(const void* src, float* dst, size_t n, int et, cudaStr
 // emd_dw.cu: TMA-fed depthwise 3x3 (stride 1) for the 16-bit modes
 bool dw_tma_supported(const DwParams& p, int et);
 cudaError_t launch_dw_tma(const DwParams& p, int et, int num_sms, cudaStream_t s);
+bool dw_s2_tma_supported(const DwParams& p, int et);   // stride 2 (cnnN_strided)
+cudaError_t launch_dw_s2_tma(const DwParams& p, int et, int num_sms, cudaStream_t s);
 bool final_tma_supported(const ConvParams& p, int et);
 cudaError_t launch_final_tma(const ConvParams& p, float scale, float shift, int et, int num_sms, cudaStream_t s);
 
