@@ -310,35 +310,50 @@ cudaError_t launch_dw3x3(const DwParams& p, int et, cudaStream_t s) {
 // optional per-channel affine + ReLU6 (the BN/ReLU6 that follows the image-level branch, DMG:345)
 // ---------------------------------------------------------------------------------------------
 template <typename T, int V>
-__global__ void __launch_bounds__(256) resize_kernel(const ResizeParams p) {
-  // thread = (output pixel, V channels); blockIdx.y = output row, blockIdx.z = image: the row's two source rows and vertical
-  // weight are block-uniform, consecutive threads walk the channels of consecutive pixels (coalesced 16-byte accesses)
+__global__ void __launch_bounds__(256) resize_kernel(const ResizeParams p, int fx) {
+  // thread = (fx consecutive output pixels of one row, V channels); blockIdx.y = output row, blockIdx.z = image.
+  // fx = out.W / in.W when that is an integer (x4 decoder upsample, x2 image-level branch, x1 BN-only steps): the fx
+  // outputs share their two source columns, so each source vector is fetched once per thread instead of once per output.
   const int C = p.in.C, cg = C / V;
   const int oy = blockIdx.y, n = blockIdx.z;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.out.W * cg) return;
-  const int ox = idx / cg, g = idx - ox * cg;
-  const float sy = oy * ((float)p.in.H / (float)p.out.H), sx = ox * ((float)p.in.W / (float)p.out.W);
-  const int y0 = (int)floorf(sy), x0 = (int)floorf(sx);
-  const int y1 = min(y0 + 1, p.in.H - 1), x1 = min(x0 + 1, p.in.W - 1);
-  const float wy = sy - y0, wx = sx - x0;
+  const int strips = p.out.W / fx;
+  if (idx >= strips * cg) return;
+  const int sx_i = idx / cg, g = idx - sx_i * cg;
+  const float ry = (float)p.in.H / (float)p.out.H, rx = (float)p.in.W / (float)p.out.W;
+  const float sy = oy * ry;
+  const int y0 = (int)floorf(sy);
+  const int y1 = min(y0 + 1, p.in.H - 1);
+  const float wy = sy - y0;
+  const int ox0 = sx_i * fx;
+  const int x0 = (int)floorf(ox0 * rx);
+  const int x1 = min(x0 + 1, p.in.W - 1);
   const T* base = reinterpret_cast<const T*>(p.in.ptr) + (size_t)n * p.in.H * p.in.W * p.in.pitch + p.in.coff + g * V;
-  float tl[V], tr[V], bl[V], br[V], o[V];
+  float tl[V], tr[V], bl[V], br[V], sc[V], sh[V];
   VecIO<T, V>::ld(base + ((size_t)y0 * p.in.W + x0) * p.in.pitch, tl);
   VecIO<T, V>::ld(base + ((size_t)y0 * p.in.W + x1) * p.in.pitch, tr);
   VecIO<T, V>::ld(base + ((size_t)y1 * p.in.W + x0) * p.in.pitch, bl);
   VecIO<T, V>::ld(base + ((size_t)y1 * p.in.W + x1) * p.in.pitch, br);
+  if (p.scale) {
 #pragma unroll
-  for (int j = 0; j < V; ++j) {
-    const float top = tl[j] + (tr[j] - tl[j]) * wx;
-    const float bot = bl[j] + (br[j] - bl[j]) * wx;
-    float v = top + (bot - top) * wy;
-    if (p.scale) v = fmaf(v, p.scale[g * V + j], p.shift[g * V + j]);
-    if (p.relu6) v = fminf(fmaxf(v, 0.f), 6.f);
-    o[j] = v;
+    for (int j = 0; j < V; ++j) { sc[j] = p.scale[g * V + j]; sh[j] = p.shift[g * V + j]; }
   }
-  T* op = reinterpret_cast<T*>(p.out.ptr) + (((size_t)n * p.out.H + oy) * p.out.W + ox) * p.out.pitch + p.out.coff + g * V;
-  VecIO<T, V>::st(op, o);
+  T* op = reinterpret_cast<T*>(p.out.ptr) + (((size_t)n * p.out.H + oy) * p.out.W + ox0) * p.out.pitch + p.out.coff + g * V;
+  for (int r = 0; r < fx; ++r) {
+    const float sx = (ox0 + r) * rx;
+    const float wx = sx - (float)x0;     // same x0 for the whole strip (fx divides the scale)
+    float o[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float top = tl[j] + (tr[j] - tl[j]) * wx;
+      const float bot = bl[j] + (br[j] - bl[j]) * wx;
+      float v = top + (bot - top) * wy;
+      if (p.scale) v = fmaf(v, sc[j], sh[j]);
+      if (p.relu6) v = fminf(fmaxf(v, 0.f), 6.f);
+      o[j] = v;
+    }
+    VecIO<T, V>::st(op + (size_t)r * p.out.pitch, o);
+  }
 }
 
 template <typename T>
@@ -348,12 +363,13 @@ static cudaError_t launch_resize_t(const ResizeParams& p, cudaStream_t s) {
   const long long px = (long long)p.N * p.out.H * p.out.W;
   (void)px;
   if (p.N > 65535 || p.out.H > 65535) return cudaErrorInvalidValue;
+  const int fx = (p.out.W % p.in.W == 0 && p.out.W / p.in.W <= 8) ? p.out.W / p.in.W : 1;
   if (sizeof(T) == 2 && al8) {
-    dim3 grid((unsigned)((p.out.W * (C / 8) + 255) / 256), (unsigned)p.out.H, (unsigned)p.N);
-    resize_kernel<T, 8><<<grid, 256, 0, s>>>(p);
+    dim3 grid((unsigned)(((p.out.W / fx) * (C / 8) + 255) / 256), (unsigned)p.out.H, (unsigned)p.N);
+    resize_kernel<T, 8><<<grid, 256, 0, s>>>(p, fx);
   } else {
-    dim3 grid((unsigned)((p.out.W * (C / 4) + 255) / 256), (unsigned)p.out.H, (unsigned)p.N);
-    resize_kernel<T, 4><<<grid, 256, 0, s>>>(p);
+    dim3 grid((unsigned)(((p.out.W / fx) * (C / 4) + 255) / 256), (unsigned)p.out.H, (unsigned)p.N);
+    resize_kernel<T, 4><<<grid, 256, 0, s>>>(p, fx);
   }
   return cudaGetLastError();
 }
