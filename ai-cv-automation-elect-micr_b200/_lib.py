@@ -38,6 +38,7 @@ SIGNATURES = {
     "emd_run_layer": (_I, [_P, C.c_char_p, _P, _P, _I, _P, _SZ, _I, _IP]),
     "emd_kernel_launches": (C.c_longlong, [_P]),
     "emd_tensor_core_launches": (C.c_longlong, [_P]),
+    "emd_graph_replays": (C.c_longlong, [_P]),
     "emd_set_tensor_cores": (_I, [_P, _I]),
     "emd_set_profile": (_I, [_P, _I]),
     "emd_num_steps": (_I, [_P]),

@@ -60,6 +60,8 @@ struct BlobEntry { uint32_t rows, cols; size_t offset; };
 
 }  // namespace
 
+struct GraphSlot { cudaGraphExec_t exec = nullptr; int calls = 0; bool failed = false; long long launches = 0, umma_launches = 0; };
+
 struct emd_engine {
   int device = 0, S = 512, variant = 0, max_batch = 1, num_sms = 148;
   cudaStream_t stream = nullptr;
@@ -87,9 +89,20 @@ struct emd_engine {
   double* d_minmax = nullptr; void* d_partial = nullptr;
   int* d_origins = nullptr;  // ys then xs, 2*256 ints
   std::vector<cudaEvent_t> events;
+  // CUDA graphs of whole passes for small batches
+  bool use_graphs = true;
+  int graph_max_n = 8;
+  std::map<int, GraphSlot> graphs;
+  float *g_in = nullptr, *g_out = nullptr;
+  long long graph_replays = 0;
 };
 
 namespace {
+
+void drop_graphs(emd_engine* e) {
+  for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  e->graphs.clear();
+}
 
 int fail(emd_engine* e, int code, const char* fmt, ...) {
   char buf[512];
@@ -302,6 +315,7 @@ void annotate_work(emd_engine* e) {
 // arena: lifetime-aware placement, greedy by size
 // ---------------------------------------------------------------------------------------------
 int plan_arena(emd_engine* e) {
+  drop_graphs(e);   // captured passes hold addresses of the old plan
   for (Tensor& t : e->tensors) { t.first = 1 << 30; t.last = -1; }
   for (int i = 0; i < (int)e->steps.size(); ++i) {
     const Step& s = e->steps[i];
@@ -629,7 +643,7 @@ cudaError_t run_step_impl(ExecCtx& c, int idx) {
   return cudaErrorInvalidValue;
 }
 
-int run_network(emd_engine* e, const float* d_in, float* d_out, int n, int mode, cudaStream_t s) {
+int run_network_direct(emd_engine* e, const float* d_in, float* d_out, int n, int mode, cudaStream_t s) {
   ExecCtx c{e, mode == EMD_MODE_FP32 ? ET_F32 : (mode == EMD_MODE_BF16 ? ET_BF16 : ET_F16), n, s, d_in, d_out, {}};
   if (e->profile && e->events.size() < e->steps.size() + 1) {
     e->events.resize(e->steps.size() + 1);
@@ -646,6 +660,50 @@ int run_network(emd_engine* e, const float* d_in, float* d_out, int n, int mode,
     CU(e, cudaStreamSynchronize(s));
     for (size_t i = 0; i < e->steps.size(); ++i) cudaEventElapsedTime(&e->steps[i].ms, e->events[i], e->events[i + 1]);
   }
+  return EMD_OK;
+}
+
+// The ~125-kernel chain of one pass is replayed from a CUDA graph for small batches, where it is launch-bound (a
+// 512x512 crop at batch 1 is ~1.6 ms of mostly launch gaps).  A graph is captured per (batch, mode) on that shape's second
+// pass (the first runs directly so every kernel's attributes are set outside capture); the network reads / writes fixed
+// staging buffers inside the graph, with a device-to-device copy of the crops either side.
+int run_network(emd_engine* e, const float* d_in, float* d_out, int n, int mode, cudaStream_t s) {
+  if (!e->use_graphs || e->profile || e->keep || n > e->graph_max_n) return run_network_direct(e, d_in, d_out, n, mode, s);
+  const int key = n * 4 + mode;
+  GraphSlot& g = e->graphs[key];
+  const size_t bytes = (size_t)n * e->S * e->S * sizeof(float);
+  if (g.calls++ == 0 || g.failed) return run_network_direct(e, d_in, d_out, n, mode, s);
+  if (!g.exec) {
+    if (!e->g_in) {
+      const size_t cap = (size_t)e->graph_max_n * e->S * e->S * sizeof(float);
+      CU(e, cudaMalloc(&e->g_in, cap));
+      CU(e, cudaMalloc(&e->g_out, cap));
+    }
+    cudaGraph_t graph = nullptr;
+    cudaError_t r = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+    int rc = EMD_OK;
+    if (r == cudaSuccess) {
+      const long long l0 = e->launches, u0 = e->umma_launches;
+      rc = run_network_direct(e, e->g_in, e->g_out, n, mode, s);
+      g.launches = e->launches - l0; g.umma_launches = e->umma_launches - u0;
+      e->launches = l0; e->umma_launches = u0;     // nothing ran yet: the replay below counts them
+      r = cudaStreamEndCapture(s, &graph);
+    }
+    if (r != cudaSuccess || rc != EMD_OK || !graph || cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
+      cudaGetLastError();
+      g.failed = true; g.exec = nullptr;
+      if (graph) cudaGraphDestroy(graph);
+      return run_network_direct(e, d_in, d_out, n, mode, s);
+    }
+    cudaGraphDestroy(graph);
+  }
+  CU(e, cudaMemcpyAsync(e->g_in, d_in, bytes, cudaMemcpyDeviceToDevice, s));
+  CU(e, cudaGraphLaunch(g.exec, s));
+  CU(e, cudaMemcpyAsync(d_out, e->g_out, bytes, cudaMemcpyDeviceToDevice, s));
+  e->last_n = n; e->last_et = mode == EMD_MODE_FP32 ? ET_F32 : (mode == EMD_MODE_BF16 ? ET_BF16 : ET_F16);
+  e->launches += g.launches;
+  e->umma_launches += g.umma_launches;
+  e->graph_replays++;
   return EMD_OK;
 }
 
@@ -693,6 +751,8 @@ int emd_create(emd_engine** out, int device, int cropsize, int variant, int max_
   e->device = device; e->S = cropsize; e->variant = variant; e->max_batch = max_batch;
   const char* env = getenv("EMD_DISABLE_UMMA");
   e->use_umma = !(env && env[0] == '1');
+  env = getenv("EMD_DISABLE_GRAPH");
+  e->use_graphs = !(env && env[0] == '1');
   env = getenv("EMD_DISABLE_TMA");
   umma_set_tma(!(env && env[0] == '1'));
   env = getenv("EMD_DISABLE_PAIR");
@@ -742,6 +802,8 @@ int emd_destroy(emd_engine* e) {
                   (void*)e->d_img, (void*)e->d_crops, (void*)e->d_tiles, (void*)e->d_sout, (void*)e->d_minmax,
                   e->d_partial, (void*)e->d_origins})
     if (p) cudaFree(p);
+  for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (e->g_in) { cudaFree(e->g_in); cudaFree(e->g_out); }
   for (auto ev : e->events) cudaEventDestroy(ev);
   if (e->copy_in) {
     cudaStreamDestroy(e->copy_in); cudaStreamDestroy(e->copy_out);
@@ -762,6 +824,7 @@ int emd_load_weights(emd_engine* e, const void* blob, size_t nbytes) {
   if (memcmp(h.magic, "EMDW0001", 8) != 0) return fail(e, EMD_EINVAL, "bad blob magic");
   if ((int)h.variant != e->variant) return fail(e, EMD_EINVAL, "blob is variant %u, engine is %d", h.variant, e->variant);
   if (nbytes < sizeof h + (size_t)h.n_entries * sizeof(BlobRecord)) return fail(e, EMD_EINVAL, "blob truncated");
+  drop_graphs(e);
   e->entries.clear();
   for (uint32_t i = 0; i < h.n_entries; ++i) {
     BlobRecord r; memcpy(&r, b + sizeof h + i * sizeof r, sizeof r);
@@ -1115,10 +1178,12 @@ int emd_run_layer(emd_engine* e, const char* name, const float* in, const float*
 
 long long emd_kernel_launches(const emd_engine* e) { return e ? e->launches : -1; }
 long long emd_tensor_core_launches(const emd_engine* e) { return e ? e->umma_launches : -1; }
+long long emd_graph_replays(const emd_engine* e) { return e ? e->graph_replays : -1; }
 
 int emd_set_tensor_cores(emd_engine* e, int on) {
   if (!e) return EMD_EINVAL;
   e->use_umma = on != 0;
+  drop_graphs(e);
   return EMD_OK;
 }
 

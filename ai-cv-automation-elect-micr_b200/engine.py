@@ -178,6 +178,10 @@ class Engine:
     def tensor_core_launches(self):
         return int(self.lib.emd_tensor_core_launches(self.h))
 
+    @property
+    def graph_replays(self):
+        return int(self.lib.emd_graph_replays(self.h))
+
     def set_tensor_cores(self, on=True):
         self._check(self.lib.emd_set_tensor_cores(self.h, int(on)), "emd_set_tensor_cores")
 

@@ -123,6 +123,30 @@ def test_batch_chunking_and_device_pointers(setup):
     assert eng.kernel_launches > 0
 
 
+def test_cuda_graph_replay_is_bit_identical(setup):
+    """Small batches are replayed from a captured CUDA graph from their third pass on: same bits as the direct passes,
+    for host and device buffers, and across a weight reload (graphs are dropped and re-captured)."""
+    eng, emd = setup["eng"], setup["emd"]
+    eng.load_weights(emd.weights.pack(setup["w1"]))
+    x = setup["crops"]
+    for mode in ("fp32", "bf16"):
+        first = eng.forward(x, mode=mode)
+        r0 = eng.graph_replays
+        outs = [eng.forward(x, mode=mode) for _ in range(4)]
+        assert eng.graph_replays >= r0 + 3
+        for o in outs:
+            np.testing.assert_array_equal(o, first)
+        t = torch.from_numpy(x).cuda()
+        d = eng.forward(t, mode=mode)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(d.cpu().numpy(), first)
+    eng.load_weights(emd.weights.pack(setup["w0"]))
+    a = eng.forward(x, mode="bf16")
+    b = [eng.forward(x, mode="bf16") for _ in range(3)][-1]
+    np.testing.assert_array_equal(a, b)
+    assert not np.array_equal(a, first)
+
+
 def test_forward_before_weights_is_an_error(emd):
     eng = emd.Engine(cropsize=32, max_batch=1)
     with pytest.raises(RuntimeError, match="emd_load_weights"):
