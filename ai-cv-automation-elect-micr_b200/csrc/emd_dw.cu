@@ -23,6 +23,7 @@ constexpr int kMathThreads = 2 * kGroupWarps * 32;   // two groups of 8 warps ta
 struct DwTmaArgs {
   DwParams p;
   int tiles_x, tiles_per_img, nchunks, items;
+  FastDiv d_chunks, d_tpi, d_tx;   // by nchunks, tiles_per_img, tiles_x
   // kReduce (final 3x3 conv 64 -> 1, DMG:531-538): p.w holds the [9][64] kernel, the 64 products are
   // summed over channels, then scale/shift, ReLU6, clip and an FP32 store
   float scale, shift;
@@ -94,10 +95,10 @@ __global__ void __launch_bounds__(kMathThreads + 32, 1) dw_tma_kernel(const __gr
   uint32_t ph = (uint32_t)((grp / kStages) & 1);
   for (int k = grp; k < my_items; k += 2) {
     const int item = blockIdx.x + k * gridDim.x;
-    const int tile = item / a.nchunks, c = item - tile * a.nchunks;
-    const int n_img = tile / a.tiles_per_img;
+    const int tile = (int)fdiv((uint32_t)item, a.d_chunks), c = item - tile * a.nchunks;
+    const int n_img = (int)fdiv((uint32_t)tile, a.d_tpi);
     const int rem = tile - n_img * a.tiles_per_img;
-    const int by = rem / a.tiles_x, bx = rem - by * a.tiles_x;
+    const int by = (int)fdiv((uint32_t)rem, a.d_tx), bx = rem - by * a.tiles_x;
     const int ch = c * kChunk + cq * 4;
     const bool ch_ok = ch < p.in.C;
     if (c != cur_c) {  // this thread's 9 x 4 depthwise weights for the chunk
@@ -122,6 +123,8 @@ __global__ void __launch_bounds__(kMathThreads + 32, 1) dw_tma_kernel(const __gr
     load_row(0, win[0]);
     load_row(1, win[1]);
     const size_t opix = ((size_t)n_img * p.out.H + by * kTH) * p.out.W + bx * kTW + col;
+    T* orow = reinterpret_cast<T*>(p.out.ptr) + opix * p.out.pitch + p.out.coff + ch;   // this thread's 4 channels of output row 0
+    const size_t ostep = (size_t)p.out.W * p.out.pitch;
 #pragma unroll
     for (int i = 0; i < kTH; ++i) {
       load_row(i + 2, win[(i + 2) % 3]);
@@ -144,8 +147,7 @@ __global__ void __launch_bounds__(kMathThreads + 32, 1) dw_tma_kernel(const __gr
           reinterpret_cast<float*>(p.out.ptr)[opix + (size_t)i * p.out.W] = v;
         }
       } else if (ch_ok) {
-        T* op = reinterpret_cast<T*>(p.out.ptr) + (opix + (size_t)i * p.out.W) * p.out.pitch + p.out.coff + ch;
-        *reinterpret_cast<uint2*>(op) = make_uint2(Up<T>::pack(acc0.x, acc0.y), Up<T>::pack(acc1.x, acc1.y));
+        *reinterpret_cast<uint2*>(orow + i * ostep) = make_uint2(Up<T>::pack(acc0.x, acc0.y), Up<T>::pack(acc1.x, acc1.y));
       }
     }
     __syncwarp();
@@ -205,10 +207,10 @@ __global__ void __launch_bounds__(kS2Groups* kS2GroupThreads + 32, 1) dw_s2_tma_
   float2 w[9][2];
   for (int k = grp; k < my_items; k += kS2Groups) {
     const int item = blockIdx.x + k * gridDim.x;
-    const int tile = item / a.nchunks, c = item - tile * a.nchunks;
-    const int n_img = tile / a.tiles_per_img;
+    const int tile = (int)fdiv((uint32_t)item, a.d_chunks), c = item - tile * a.nchunks;
+    const int n_img = (int)fdiv((uint32_t)tile, a.d_tpi);
     const int rem = tile - n_img * a.tiles_per_img;
-    const int by = rem / a.tiles_x, bx = rem - by * a.tiles_x;
+    const int by = (int)fdiv((uint32_t)rem, a.d_tx), bx = rem - by * a.tiles_x;
     const int ch = c * kChunk + cq * 4;
     const bool ch_ok = ch < p.in.C;
     if (c != cur_c) {
@@ -232,6 +234,8 @@ __global__ void __launch_bounds__(kS2Groups* kS2GroupThreads + 32, 1) dw_s2_tma_
     };
     load_row(0, win[0]);
     const size_t opix = ((size_t)n_img * p.out.H + by * kS2T) * p.out.W + bx * kS2T + col;
+    T* orow = reinterpret_cast<T*>(p.out.ptr) + opix * p.out.pitch + p.out.coff + ch;
+    const size_t ostep = (size_t)p.out.W * p.out.pitch;
 #pragma unroll
     for (int i = 0; i < kS2T; ++i) {
       // window rows for output row i: halo rows 2i, 2i+1, 2i+2 live in win[(2i)%3], win[(2i+1)%3], win[(2i+2)%3]
@@ -243,10 +247,7 @@ __global__ void __launch_bounds__(kS2Groups* kS2GroupThreads + 32, 1) dw_s2_tma_
         acc0 = ptx::ffma2(win[(2 * i + t / 3) % 3][t % 3][0], w[t][0], acc0);
         acc1 = ptx::ffma2(win[(2 * i + t / 3) % 3][t % 3][1], w[t][1], acc1);
       }
-      if (ch_ok) {
-        T* op = reinterpret_cast<T*>(p.out.ptr) + (opix + (size_t)i * p.out.W) * p.out.pitch + p.out.coff + ch;
-        *reinterpret_cast<uint2*>(op) = make_uint2(Up<T>::pack(acc0.x, acc0.y), Up<T>::pack(acc1.x, acc1.y));
-      }
+      if (ch_ok) *reinterpret_cast<uint2*>(orow + i * ostep) = make_uint2(Up<T>::pack(acc0.x, acc0.y), Up<T>::pack(acc1.x, acc1.y));
     }
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(bar_empty + 8u * grp);
@@ -283,6 +284,7 @@ static cudaError_t launch_common(DwTmaArgs& a, int et, bool reduce, int num_sms,
   a.tiles_per_img = (p.OH / kTH) * a.tiles_x;
   a.nchunks = (p.in.C + kChunk - 1) / kChunk;
   a.items = p.N * a.tiles_per_img * a.nchunks;
+  a.d_chunks = make_fastdiv((uint32_t)a.nchunks); a.d_tpi = make_fastdiv((uint32_t)a.tiles_per_img); a.d_tx = make_fastdiv((uint32_t)a.tiles_x);
   CUtensorMap tmap;
   void* base = reinterpret_cast<char*>(p.in.ptr) + (size_t)p.in.coff * 2;
   if (!tma_encode_nhwc(&tmap, et == ET_BF16, base, p.in.C, p.in.W, p.in.H, p.N, p.in.pitch, kChunk, kHaloW, kHaloH, 1, false))
@@ -330,6 +332,7 @@ cudaError_t launch_dw_s2_tma(const DwParams& p, int et, int num_sms, cudaStream_
   a.tiles_per_img = (p.OH / kS2T) * a.tiles_x;
   a.nchunks = (p.in.C + kChunk - 1) / kChunk;
   a.items = p.N * a.tiles_per_img * a.nchunks;
+  a.d_chunks = make_fastdiv((uint32_t)a.nchunks); a.d_tpi = make_fastdiv((uint32_t)a.tiles_per_img); a.d_tx = make_fastdiv((uint32_t)a.tiles_x);
   CUtensorMap tmap;
   void* base = reinterpret_cast<char*>(p.in.ptr) + (size_t)p.in.coff * 2;
   if (!tma_encode_nhwc(&tmap, et == ET_BF16, base, p.in.C, p.in.W, p.in.H, p.N, p.in.pitch, kChunk, kS2Halo, kS2Halo, 1, false))

@@ -43,21 +43,6 @@ constexpr int kMathThreads = 512;                           // two groups of 8 w
 constexpr int kGroupWarps = 8;
 constexpr int kMaxStages = 8;
 
-// unsigned division by a runtime constant (Granlund-Montgomery): q = (t + ((x - t) >> 1)) >> (l - 1), t = mulhi(m, x)
-struct FastDiv { uint32_t d, m, l; };
-inline FastDiv make_fastdiv(uint32_t d) {
-  FastDiv f;
-  f.d = d; f.l = 0;
-  while ((1ull << f.l) < d) ++f.l;
-  f.m = (uint32_t)((((1ull << f.l) - d) << 32) / d + 1);
-  return f;
-}
-__device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv& f) {
-  if (f.d == 1) return x;
-  const uint32_t t = __umulhi(f.m, x);
-  return (t + ((x - t) >> 1)) >> (f.l - 1);
-}
-
 struct FusedArgs {
   ConvParams p;
   NTiling nt;

@@ -9,6 +9,23 @@
 
 namespace emd {
 
+// unsigned division by a runtime constant (Granlund-Montgomery): q = (t + ((x - t) >> 1)) >> (l - 1), t = mulhi(m, x)
+struct FastDiv { uint32_t d, m, l; };
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d; f.l = 0;
+  while ((1ull << f.l) < d) ++f.l;
+  f.m = (uint32_t)((((1ull << f.l) - d) << 32) / d + 1);
+  return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv& f) {
+  if (f.d == 1) return x;
+  const uint32_t t = __umulhi(f.m, x);
+  return (t + ((x - t) >> 1)) >> (f.l - 1);
+}
+#endif
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
