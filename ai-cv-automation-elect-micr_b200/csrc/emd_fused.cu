@@ -37,8 +37,10 @@ constexpr int kSlabBytes = kBM * 64 * 2;                    // 128 pixels x 64 c
 constexpr int kMaxRing = 3;
 constexpr int kMaxC = 768;
 constexpr int kSmemLimit = 227 * 1024;
-constexpr int kEpiThreads = 128;
-constexpr int kBaseThreads = 192;                           // epilogue + MMA + producer
+// epilogue warps: 4 in dw mode (the register file goes to the 16 math warps), 8 in taps mode where two warps share each TMEM
+// lane quadrant and split every 64-column slab in halves (output-heavy layers were bound by the epilogue's serial chain)
+constexpr int epi_warps(bool dw) { return dw ? 4 : 8; }
+constexpr int base_threads(bool dw) { return epi_warps(dw) * 32 + 64; }   // epilogue + MMA + producer
 constexpr int kMathThreads = 512;                           // two groups of 8 warps, alternating chunks
 constexpr int kGroupWarps = 8;
 constexpr int kMaxStages = 8;
@@ -158,7 +160,7 @@ __device__ __forceinline__ void epi_half(const uint32_t (&v)[32], const float* _
 struct OutMaps { CUtensorMap m[4]; };   // output tensor map per variant
 
 template <typename T, bool kDw, bool kRes, bool kPair>
-__global__ void __launch_bounds__(kDw ? kBaseThreads + kMathThreads : kBaseThreads, 1)
+__global__ void __launch_bounds__(kDw ? base_threads(true) + kMathThreads : base_threads(false), 1)
 fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ CUtensorMap tmap_in,
                   const __grid_constant__ OutMaps tmaps_out, const __grid_constant__ CUtensorMap tmap_res,
                   const __grid_constant__ CUtensorMap tmap_w) {
@@ -185,6 +187,8 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 * kMaxStages + 4 + kMaxRing);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kEpiWarps = epi_warps(kDw), kEpiThreads = kEpiWarps * 32, kBaseThreads = base_threads(kDw);
+  constexpr int kMmaWarp = kEpiWarps, kProdWarp = kEpiWarps + 1;
   // pair mode: the cluster (not the CTA) walks the item list; an item covers M tiles 2m and 2m+1 (one per CTA of the pair)
   uint32_t crank = 0;
   if constexpr (kPair) crank = cluster_ctarank();
@@ -214,14 +218,14 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
       mbar_init(bar_hfull + 8u * s, 1);
       mbar_init(bar_hempty + 8u * s, kGroupWarps);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, (kPair ? 2 : 1) * kEpiThreads / 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, (kPair ? 2 : 1) * kEpiWarps); }
     for (int i = 0; i < kMaxRing; ++i) mbar_init(bar_rfull + 8u * i, 1);
     fence_barrier_init();
     prefetch_tmap(&tmap_in);
     for (int v = 0; v < a.nvar; ++v) prefetch_tmap(&tmaps_out.m[v]);
     if (kRes) prefetch_tmap(&tmap_res);
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     if constexpr (kPair) tmem_alloc_2sm(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
     else tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
   }
@@ -231,7 +235,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 5) {
+  if (warp == kProdWarp) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       const char* wbase = reinterpret_cast<const char*>(p.w16);
@@ -291,7 +295,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     Ring ra(0, SA), rb(0, SB);
     int tcount = 0;
@@ -340,11 +344,14 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
         if (++c == a.nchunks) c = 0;
       }
     }
-  } else if (warp < 4) {
-    // ===================== epilogue (warp w owns TMEM lanes 32w..32w+31 = pixel rows of the tile) =====================
-    const int tid = threadIdx.x;             // 0..127 = row of the tile
-    const uint32_t row_off = (uint32_t)tid * 128u;
-    const int rsw = tid & 7;
+  } else if (warp < kEpiWarps) {
+    // ===================== epilogue (warp w reads TMEM lanes 32(w%4).. = pixel rows of the tile; with 8 warps, warps w and
+    // w+4 take the two 32-column halves of every slab) =====================
+    const int tid = threadIdx.x;
+    const int row = (warp & 3) * 32 + lane;  // row of the tile
+    const int my_half = warp >> 2;           // 8-warp mode: the half of each slab this warp converts
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const int rsw = row & 7;
     // residual prefetch cursor (thread 0): slab sequence number -> (tile, slab)
     int pf_tile = first, pf_slab = 0, pf_buf = 0;
     auto prefetch_res = [&]() {
@@ -372,7 +379,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
       const int acc = tcount & 1;
       mbar_wait(bar_tfull + 8u * acc, (uint32_t)((tcount >> 1) & 1));
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * a.acc_stride);
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(acc * a.acc_stride);
       const int nslabs = (n + 63) >> 6;
       for (int j = 0; j < nslabs; ++j) {
         const int buf = rq.idx;
@@ -381,15 +388,18 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c0 = j * 64 + h * 32;        // column within the N tile
-          if (c0 < n) {
-            uint32_t v[32];
+          const bool mine = kEpiWarps == 4 || h == my_half;
+          uint32_t v[32];
+          if (mine && c0 < n) {
             tmem_ld32(taddr + (uint32_t)c0, v);
             tmem_ld_wait();
-            if (j == nslabs - 1 && (h == 1 || c0 + 32 >= n)) {  // last read of this accumulator: hand it back to the MMA warp
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) { if constexpr (kPair) mbar_arrive_leader(bar_tempty + 8u * acc); else mbar_arrive(bar_tempty + 8u * acc); }
-            }
+          }
+          if (j == nslabs - 1 && h == 1) {       // this warp's last read of the accumulator is done: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if constexpr (kPair) mbar_arrive_leader(bar_tempty + 8u * acc); else mbar_arrive(bar_tempty + 8u * acc); }
+          }
+          if (mine && c0 < n) {
             if (p.relu6) epi_half<T, kRes, true>(v, s_scale + n0 + c0, s_shift + n0 + c0, srow, h, rsw);
             else epi_half<T, kRes, false>(v, s_scale + n0 + c0, s_shift + n0 + c0, srow, h, rsw);
           }
@@ -479,7 +489,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
   tc_fence_before();
   __syncthreads();
   if constexpr (kPair) cluster_sync_all();      // neither CTA retires while the other may still signal its barriers or read its smem
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     if constexpr (kPair) tmem_dealloc_2sm(tmem_base, (uint32_t)a.tmem_cols);
     else tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
@@ -502,7 +512,7 @@ cudaError_t launch_t(const FusedArgs& a, const CUtensorMap& tin, const OutMaps& 
     if (r != cudaSuccess) return r;
     attr_dev = dev;
   }
-  const int block = kDw ? kBaseThreads + kMathThreads : kBaseThreads;
+  const int block = kDw ? base_threads(true) + kMathThreads : base_threads(false);
   if (kPair) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
