@@ -12,7 +12,7 @@
 //              warps slide the 3x3 window in registers (FP32, packed FFMA2) and write the 16-bit result
 //              straight into the swizzled A stage -- the depthwise intermediate never goes to HBM.
 //
-// Warp roles: 0-3 epilogue, 4 MMA issuer, 5 TMA producer, 6-13 depthwise math (dw mode only).
+// Warp roles: 0-7 epilogue, 8 MMA issuer, 9 TMA producer, 10-25 depthwise math (dw mode only).
 // Epilogue: tcgen05.ld (one pixel row per thread) -> folded BN scale/shift (FFMA2) -> ReLU6 -> (+ residual,
 // which a TMA load has already put into the output staging slab) -> 16-bit pack -> swizzled smem slab of
 // 128 px x 64 ch -> one TMA store per slab (clipped at the view's channel count; a channel slice of a concat
@@ -37,9 +37,9 @@ constexpr int kSlabBytes = kBM * 64 * 2;                    // 128 pixels x 64 c
 constexpr int kMaxRing = 3;
 constexpr int kMaxC = 768;
 constexpr int kSmemLimit = 227 * 1024;
-// epilogue warps: 4 in dw mode (the register file goes to the 16 math warps), 8 in taps mode where two warps share each TMEM
-// lane quadrant and split every 64-column slab in halves (output-heavy layers were bound by the epilogue's serial chain)
-constexpr int epi_warps(bool dw) { return dw ? 4 : 8; }
+// epilogue warps: two per TMEM lane quadrant, each converting one 32-column half of every 64-column slab (with 4 warps the
+// output-heavy layers were bound by the epilogue's serial chain); dw mode still fits 16 math warps at 72 registers
+constexpr int epi_warps(bool) { return 8; }
 constexpr int base_threads(bool dw) { return epi_warps(dw) * 32 + 64; }   // epilogue + MMA + producer
 constexpr int kMathThreads = 512;                           // two groups of 8 warps, alternating chunks
 constexpr int kGroupWarps = 8;
