@@ -5,3 +5,4 @@ from .denoiser import Denoiser, scale0to1  # noqa: F401
 from .engine import Engine  # noqa: F401
 from . import weights  # noqa: F401
 from . import sharding  # noqa: F401
+from . import tfckpt  # noqa: F401

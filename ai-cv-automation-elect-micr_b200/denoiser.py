@@ -19,6 +19,7 @@ import numpy as np
 
 from .engine import Engine
 from . import weights as _weights
+from . import tfckpt as _tfckpt
 
 CROPSIZE = 512  # misc_py/denoiser-multi-gpu.py:112
 
@@ -56,9 +57,10 @@ def _resize_bilinear(img, size):
 class Denoiser(object):
     """Creates denoiser instance (DEN:584-630).
 
-    checkpoint_loc: a packed weight blob file written by ``weights.pack`` (``*.emdw``), a dict of
-        reference variables (see weights.py), or None for a fresh graph's initial values
-        (``weights.init_reference_weights``) -- reading TF checkpoints is a "next" item.
+    checkpoint_loc: like the reference, a TensorFlow checkpoint DIRECTORY (its latest checkpoint is restored,
+        DEN:626-627) or a checkpoint prefix (``.../model.ckpt-1234``), read by ``tfckpt`` without TensorFlow; also
+        a packed weight blob file written by ``weights.pack`` (``*.emdw``), a dict of reference variables (see
+        weights.py), or None for a fresh graph's initial values (``weights.init_reference_weights``).
     visible_cuda: like the reference, a string put into CUDA_VISIBLE_DEVICES (DEN:591); None leaves
         the environment alone (the reference raises TypeError there, App. D).
     Extra keyword arguments (not in the reference): device, mode ('bf16' | 'fp16' | 'fp32'),
@@ -81,6 +83,8 @@ class Denoiser(object):
             blob = _weights.pack(checkpoint_loc, variant)
         elif isinstance(checkpoint_loc, (bytes, bytearray)):
             blob = bytes(checkpoint_loc)
+        elif os.path.isdir(checkpoint_loc) or os.path.exists(str(checkpoint_loc) + ".index"):
+            blob = _weights.pack(_tfckpt.load_params(str(checkpoint_loc), variant), variant)
         else:
             with open(checkpoint_loc, "rb") as f:
                 blob = f.read()

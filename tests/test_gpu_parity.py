@@ -237,6 +237,17 @@ def test_denoiser_dropin_api(emd, setup):
         d.denoise(np.zeros((S - 1, S)))  # smaller than a crop
 
 
+def test_denoiser_restores_tf_checkpoint_directory(emd, setup, tmp_path):
+    """Denoiser(checkpoint_loc=<TF checkpoint directory>) -- the reference's constructor semantics (DEN:588, 626-627):
+    the latest checkpoint is read without TensorFlow and gives bit-identical results to the same variables passed directly."""
+    from tf_bundle_writer import write_checkpoint
+    variables = {t: setup["w1"][p] for t, p in emd.tfckpt.tf_variable_names("A")}
+    write_checkpoint(str(tmp_path / "model.ckpt-7"), variables)
+    a = emd.Denoiser(checkpoint_loc=str(tmp_path), mode="bf16", cropsize=S, max_batch=4)
+    b = emd.Denoiser(checkpoint_loc=setup["w1"], mode="bf16", cropsize=S, max_batch=4)
+    assert np.array_equal(a.denoise_crops(setup["crops"]), b.denoise_crops(setup["crops"]))
+
+
 # ---- variant B: the graph of the deployed class file (machine_learning/denoiser.py:58-398) --------------------
 
 def test_variant_b_fp32_and_bf16(emd):
