@@ -240,7 +240,49 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
     if (lane == 0) {
       const char* wbase = reinterpret_cast<const char*>(p.w16);
       Ring ra(0, SA), rb(0, SB), rh(0, kDw ? SH : 1);
-      for (int tile = first; tile < total_tiles; tile += step) {
+      if constexpr (kDw) {
+        // Two independent cursors over this CTA's (tile, chunk) items: halo tiles run ahead as far as the halo ring allows,
+        // weight blocks follow the MMA's consumption.  (One in-order stream would hold every halo behind a weight slot that
+        // only frees when an MMA retires, i.e. limit the halo prefetch distance to the weight ring's depth.)
+        int h_tile = first, h_c = 0, b_tile = first, b_c = 0;
+        int h_img = 0, h_y0 = 0, h_x0 = 0;
+        uint32_t b_bytes = 0;
+        const char* b_src = nullptr;
+        bool h_new = true, b_new = true;
+        while (h_tile < total_tiles || b_tile < total_tiles) {
+          if (h_tile < total_tiles) {
+            if (h_new) {
+              int mt, ntile, var;
+              split(h_tile, mt, ntile, var);
+              tile_coords(a, mt, h_img, h_y0, h_x0);
+              h_new = false;
+            }
+            if (mbar_test(bar_hempty + 8u * rh.idx, rh.phase ^ 1u)) {
+              mbar_arrive_expect_tx(bar_hfull + 8u * rh.idx, kHaloBytes);
+              tma_load_4d(sH + (uint32_t)rh.idx * kHaloBytes, &tmap_in, h_c * kBK, h_x0 - 1, h_y0 - 1, h_img, bar_hfull + 8u * rh.idx);
+              rh.advance(1);
+              if (++h_c == a.nchunks) { h_c = 0; h_tile += step; h_new = true; }
+            }
+          }
+          if (b_tile < total_tiles) {
+            if (b_new) {
+              int mt, ntile, var;
+              split(b_tile, mt, ntile, var);
+              b_bytes = (uint32_t)a.nt.rows[ntile] * 128u;
+              b_src = wbase + (size_t)a.nt.rows_before[ntile] * a.w_kblocks * 128 + (size_t)(a.v_wrow[0][0] * a.nchunks) * b_bytes;
+              b_new = false;
+            }
+            if (mbar_test(bar_bempty + 8u * rb.idx, rb.phase ^ 1u)) {
+              mbar_arrive_expect_tx(bar_bfull + 8u * rb.idx, b_bytes);
+              bulk_g2s(sB + (uint32_t)rb.idx * a.b_stage_bytes, b_src, b_bytes, bar_bfull + 8u * rb.idx);
+              b_src += b_bytes;
+              rb.advance(1);
+              if (++b_c == a.nchunks) { b_c = 0; b_tile += step; b_new = true; }
+            }
+          }
+        }
+      }
+      for (int tile = first; !kDw && tile < total_tiles; tile += step) {
         int mt, ntile, var;
         split(tile, mt, ntile, var);
         const int ntaps = a.v_ntaps[var];
@@ -249,19 +291,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
         const char* tbase = wbase + (size_t)a.nt.rows_before[ntile] * a.w_kblocks * 128;
         int n_img, y0, x0;
         tile_coords(a, mt, n_img, y0, x0);
-        if (kDw) {
-          const char* wsrc = tbase + (size_t)(a.v_wrow[0][0] * a.nchunks) * bytes;
-          for (int c = 0; c < a.nchunks; ++c) {
-            mbar_wait(bar_hempty + 8u * rh.idx, rh.phase ^ 1u);
-            mbar_arrive_expect_tx(bar_hfull + 8u * rh.idx, kHaloBytes);
-            tma_load_4d(sH + (uint32_t)rh.idx * kHaloBytes, &tmap_in, c * kBK, x0 - 1, y0 - 1, n_img, bar_hfull + 8u * rh.idx);
-            mbar_wait(bar_bempty + 8u * rb.idx, rb.phase ^ 1u);
-            mbar_arrive_expect_tx(bar_bfull + 8u * rb.idx, bytes);
-            bulk_g2s(sB + (uint32_t)rb.idx * a.b_stage_bytes, wsrc, bytes, bar_bfull + 8u * rb.idx);
-            wsrc += bytes;
-            rh.advance(1); rb.advance(1);
-          }
-        } else {
+        {
           const int xb = x0 * p.istride, yb = y0 * p.istride;
           if (a.b_res && tile == first) {   // first tile of this CTA: bring in every weight block, once
             mbar_arrive_expect_tx(bar_bfull, bytes * (uint32_t)(ntaps * a.nchunks));
@@ -610,13 +640,23 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
   // stage counts from the shared-memory budget
   a.ring = kMaxRing;
   if (a.dw_mode) {
-    a.SA = a.SB = a.SH = 4;
+    // Each of the two math groups holds one halo and one A stage at a time, so A needs one spare stage and the halo ring
+    // wants everything that is left: the halo tiles are the HBM stream, and their prefetch distance is SH - 2 items.
+    // The output ring only needs its third slab where a residual is prefetched into it.
+    a.SA = 3; a.SB = 3; a.SH = 6;
+    a.ring = a.has_res ? kMaxRing : 2;
+    static const int t_sa = getenv("EMD_DW_SA") ? atoi(getenv("EMD_DW_SA")) : 0, t_sb = getenv("EMD_DW_SB") ? atoi(getenv("EMD_DW_SB")) : 0,
+                     t_sh = getenv("EMD_DW_SH") ? atoi(getenv("EMD_DW_SH")) : 0, t_ring = getenv("EMD_DW_RING") ? atoi(getenv("EMD_DW_RING")) : 0;   // tuning switches
+    if (t_sa) a.SA = t_sa;
+    if (t_sb) a.SB = t_sb;
+    if (t_sh) a.SH = t_sh;
+    if (t_ring) a.ring = t_ring;
     while (fused_smem_bytes(a) > (size_t)kSmemLimit) {
+      if (a.SH > 4) { --a.SH; continue; }
       if (a.ring == 3 && a.nt.maxrows > 128) { a.ring = 2; continue; }
-      if (a.SB >= a.SA && a.SB >= a.SH && a.SB > 2) { --a.SB; continue; }
-      if (a.SH >= a.SA && a.SH > 2) { --a.SH; continue; }
-      if (a.SA > 2) { --a.SA; continue; }
       if (a.SB > 2) { --a.SB; continue; }
+      if (a.SH > 2) { --a.SH; continue; }
+      if (a.SA > 2) { --a.SA; continue; }
       if (a.ring == 3) { a.ring = 2; continue; }
       return cudaErrorInvalidValue;
     }

@@ -41,6 +41,23 @@ __global__ void __launch_bounds__(512) k(float* out, long long* cycles, int iter
       } else if (OP == 5) {  // LOP3 and-mask
 #pragma unroll
         for (int i = 0; i < 8; ++i) u[i] = (u[i] & 0xffff0000u) | u[(i + 3) & 7];
+      } else if (OP == 7) {  // FHFMA.BF16: fp32 += bf16 * bf16 (mixed-precision fma, PTX 8.6, sm_100+), low halves
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          unsigned short xl, xh, wl, wh;
+          asm("mov.b32 {%0,%1}, %2;" : "=h"(xl), "=h"(xh) : "r"(u[i]));
+          asm("mov.b32 {%0,%1}, %2;" : "=h"(wl), "=h"(wh) : "r"(u[(i + 1) & 7]));
+          asm volatile("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(a[i]) : "h"(xl), "h"(wl));
+        }
+      } else if (OP == 8) {  // FHFMA.BF16 alternating low / high halves (the depthwise pattern)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          unsigned short xl, xh, wl, wh;
+          asm("mov.b32 {%0,%1}, %2;" : "=h"(xl), "=h"(xh) : "r"(u[i & 3]));
+          asm("mov.b32 {%0,%1}, %2;" : "=h"(wl), "=h"(wh) : "r"(u[4 + (i & 3)]));
+          if (i & 4) asm volatile("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(a[i]) : "h"(xh), "h"(wh));
+          else asm volatile("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(a[i]) : "h"(xl), "h"(wl));
+        }
       } else if (OP == 6) {  // HFMA2 fp16
 #pragma unroll
         for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(u[i]) : "r"(__float_as_uint(w0)), "r"(__float_as_uint(b[i])));
@@ -76,6 +93,8 @@ template <int OP> void run(const char* name, int ops_per_iter) {
 int main() {
   run<0>("FFMA", 64);
   run<1>("FFMA2", 32);
+  run<7>("FHFMA.BF16", 64);
+  run<8>("FHFMA.BF16 l/h", 64);
   run<2>("HFMA2.BF16", 64);
   run<6>("HFMA2.F16", 64);
   run<3>("SHL16+XOR", 64);
