@@ -479,6 +479,10 @@ cudaError_t run_conv(ExecCtx& c, ConvParams& p, const Step& s) {
   e->launches++;
   if (c.et != ET_F32 && e->use_umma && final_tma_supported(p, c.et)) {
     p.w = s.wr[c.et];
+    if (final_umma_supported(p, c.et)) {
+      e->umma_launches++;
+      return launch_final_umma(p, s.scale0, s.shift0, c.et, e->num_sms, c.s);
+    }
     return launch_final_tma(p, s.scale0, s.shift0, c.et, e->num_sms, c.s);
   }
   if (c.et != ET_F32 && e->use_umma && s.w16[c.et] && fused_supported(p, c.et, nullptr)) {

@@ -90,6 +90,9 @@ bool dw_s2_tma_supported(const DwParams& p, int et);   // stride 2 (cnnN_strided
 cudaError_t launch_dw_s2_tma(const DwParams& p, int et, int num_sms, cudaStream_t s);
 bool final_tma_supported(const ConvParams& p, int et);
 cudaError_t launch_final_tma(const ConvParams& p, float scale, float shift, int et, int num_sms, cudaStream_t s);
+// same layer on the tensor cores (emd_final.cu): channel reduction as a per-tile GEMM over the halo, then a 9-tap gather
+bool final_umma_supported(const ConvParams& p, int et);
+cudaError_t launch_final_umma(const ConvParams& p, float scale, float shift, int et, int num_sms, cudaStream_t s);
 
 // Split of the output channels into UMMA N tiles (<= 256 columns each, multiples of 16); the packed
 // B operand (umma_pack_weights) and both tcgen05 kernels share it.

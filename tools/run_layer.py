@@ -27,7 +27,7 @@ def main():
     spec = {l[0]: l for l in emd.weights.layer_table("A")}[a.layer]
     dims = (C.c_int * 4)()
     probe = np.zeros((1,), np.float32)
-    eng.lib.emd_run_layer(eng.h, a.layer.encode(), probe.ctypes.data_as(C.c_void_p), None, a.n, None, 0,
+    eng.lib.emd_run_layer(eng.h, a.layer.encode(), probe.ctypes.data_as(C.c_void_p), probe.ctypes.data_as(C.c_void_p), a.n, None, 0,
                           emd._lib.MODES[a.mode], dims)
     oh, ow, oc = dims[1], dims[2], dims[3]
     cin = spec[2]
