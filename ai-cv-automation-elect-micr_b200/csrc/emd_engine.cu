@@ -81,6 +81,9 @@ struct emd_engine {
   float *d_stage_in = nullptr, *d_stage_out = nullptr;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of emd_forward with host buffers
   cudaEvent_t ev_in[2] = {}, ev_done[2] = {}, ev_out[2] = {}, ev_start = nullptr;
+  int last_input_step = 0;                                // last step that reads the network input
+  static constexpr int kSlices = 8;                       // sliced first / last step of a pass (emd_forward, host buffers)
+  cudaEvent_t ev_sl_in[kSlices] = {}, ev_sl_fin[kSlices] = {}, ev_in_free = nullptr, ev_out_free = nullptr;
   // whole-image pipeline buffers (grown on demand)
   void* d_img_raw = nullptr; size_t img_raw_bytes = 0;
   float* d_img = nullptr; size_t img_bytes = 0;
@@ -460,6 +463,7 @@ struct ExecCtx {
   const float* d_in;  // network input (device, f32)
   float* d_out;       // network output (device, f32)
   std::vector<Override> ov;
+  int b0 = 0;         // first crop of the batch this step works on (a slice of the batch: every view starts b0 images in)
 };
 
 View make_view(const ExecCtx& c, Ref r) {
@@ -468,9 +472,11 @@ View make_view(const ExecCtx& c, Ref r) {
   for (const Override& o : c.ov)
     if (o.t == r.t) { v.ptr = o.ptr; v.pitch = r.C; v.coff = 0; return v; }
   v.pitch = t.C; v.coff = r.coff;
+  size_t esz = 4;     // network input and output are FP32 images
   if (r.t == c.e->t_input) v.ptr = const_cast<float*>(c.d_in);
   else if (r.t == c.e->t_output) v.ptr = c.d_out;
-  else v.ptr = c.e->arena + t.offset;
+  else { v.ptr = c.e->arena + t.offset; esz = c.et == ET_F32 ? 4 : 2; }
+  if (c.b0) v.ptr = reinterpret_cast<char*>(v.ptr) + (size_t)c.b0 * t.H * t.W * t.C * esz;
   return v;
 }
 
@@ -667,6 +673,66 @@ int run_network_direct(emd_engine* e, const float* d_in, float* d_out, int n, in
   return EMD_OK;
 }
 
+// One pass over a large batch with HOST input and / or output: only the first step reads the crops and only the last one
+// writes the result, so those two run slice by slice -- the first step on slice q as soon as its H2D copy has landed, the
+// D2H copy of slice q as soon as the last step has written it -- and everything in between runs once on the whole batch.
+// Exposed copy time is one slice each way instead of one chunk, and the network keeps its full-batch efficiency.
+// h_in / h_out null = that side is already on the device (d_in / d_out used as given).
+int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const float* d_in, float* d_out, int n, int mode,
+                       cudaStream_t s, bool first_pass) {
+  ExecCtx c{e, mode == EMD_MODE_FP32 ? ET_F32 : (mode == EMD_MODE_BF16 ? ET_BF16 : ET_F16), n, s, d_in, d_out, {}};
+  const size_t per = (size_t)e->S * e->S;
+  static const int k_env = getenv("EMD_IO_SLICES") ? atoi(getenv("EMD_IO_SLICES")) : 0;   // tuning switch
+  const int K = k_env > 0 && k_env <= emd_engine::kSlices ? k_env : emd_engine::kSlices;
+  const int qs = (n + K - 1) / K, last = (int)e->steps.size() - 1;
+  int head = 1;         // the steps of the first layer (its depthwise and pointwise halves)
+  while (head < last && e->steps[head].layer == e->steps[0].layer) ++head;
+  int in_free_at = head;   // the step after which the staging copy of the crops is dead (a fused depthwise reads at the next step)
+  for (int i = head; i < last; ++i)
+    if (e->steps[i].in.t == e->t_input) in_free_at = std::min(i + 1, last - 1);
+  e->last_n = n; e->last_et = c.et;
+  auto step = [&](int i, int b0, int nb) -> int {
+    c.b0 = b0; c.n = nb;
+    cudaError_t r = run_step(c, i);
+    c.b0 = 0; c.n = n;
+    return r == cudaSuccess ? EMD_OK : fail(e, EMD_ECUDA, "step %s: %s", e->steps[i].name.c_str(), cudaGetErrorString(r));
+  };
+  int rc;
+  if (h_in) {
+    if (!first_pass) CU(e, cudaStreamWaitEvent(e->copy_in, e->ev_in_free, 0));      // the pass before has read the staging buffer
+    for (int q = 0; q * qs < n; ++q) {
+      const int b0 = q * qs, nb = std::min(qs, n - b0);
+      CU(e, cudaMemcpyAsync(const_cast<float*>(d_in) + b0 * per, h_in + b0 * per, nb * per * 4, cudaMemcpyHostToDevice, e->copy_in));
+      CU(e, cudaEventRecord(e->ev_sl_in[q], e->copy_in));
+    }
+    for (int q = 0; q * qs < n; ++q) {
+      const int b0 = q * qs, nb = std::min(qs, n - b0);
+      CU(e, cudaStreamWaitEvent(s, e->ev_sl_in[q], 0));
+      for (int i = 0; i < head; ++i)
+        if ((rc = step(i, b0, nb))) return rc;
+    }
+  } else {
+    for (int i = 0; i < head; ++i)
+      if ((rc = step(i, 0, n))) return rc;
+  }
+  for (int i = head; i < last; ++i) {
+    if ((rc = step(i, 0, n))) return rc;
+    if (h_in && i == in_free_at) CU(e, cudaEventRecord(e->ev_in_free, s));   // nothing later reads the crops
+  }
+  if (h_out) {
+    if (!first_pass) CU(e, cudaStreamWaitEvent(s, e->ev_out_free, 0));              // the D2H copies of the pass before have drained
+    for (int q = 0; q * qs < n; ++q) {
+      const int b0 = q * qs, nb = std::min(qs, n - b0);
+      if ((rc = step(last, b0, nb))) return rc;
+      CU(e, cudaEventRecord(e->ev_sl_fin[q], s));
+      CU(e, cudaStreamWaitEvent(e->copy_out, e->ev_sl_fin[q], 0));
+      CU(e, cudaMemcpyAsync(h_out + b0 * per, d_out + b0 * per, nb * per * 4, cudaMemcpyDeviceToHost, e->copy_out));
+    }
+    CU(e, cudaEventRecord(e->ev_out_free, e->copy_out));
+  } else if ((rc = step(last, 0, n))) return rc;
+  return EMD_OK;
+}
+
 // The ~125-kernel chain of one pass is replayed from a CUDA graph for small batches, where it is launch-bound (a
 // 512x512 crop at batch 1 is ~1.6 ms of mostly launch gaps).  A graph is captured per (batch, mode) on that shape's second
 // pass (the first runs directly so every kernel's attributes are set outside capture); the network reads / writes fixed
@@ -813,6 +879,8 @@ int emd_destroy(emd_engine* e) {
     cudaStreamDestroy(e->copy_in); cudaStreamDestroy(e->copy_out);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(e->ev_in[i]); cudaEventDestroy(e->ev_done[i]); cudaEventDestroy(e->ev_out[i]); }
     cudaEventDestroy(e->ev_start);
+    for (int i = 0; i < emd_engine::kSlices; ++i) { cudaEventDestroy(e->ev_sl_in[i]); cudaEventDestroy(e->ev_sl_fin[i]); }
+    cudaEventDestroy(e->ev_in_free); cudaEventDestroy(e->ev_out_free);
   }
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -878,10 +946,33 @@ int emd_forward(emd_engine* e, const float* crops, int n, float* out, int mode, 
       CU(e, cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
     }
     CU(e, cudaEventCreateWithFlags(&e->ev_start, cudaEventDisableTiming));
+    for (int i = 0; i < emd_engine::kSlices; ++i) {
+      CU(e, cudaEventCreateWithFlags(&e->ev_sl_in[i], cudaEventDisableTiming));
+      CU(e, cudaEventCreateWithFlags(&e->ev_sl_fin[i], cudaEventDisableTiming));
+    }
+    CU(e, cudaEventCreateWithFlags(&e->ev_in_free, cudaEventDisableTiming));
+    CU(e, cudaEventCreateWithFlags(&e->ev_out_free, cudaEventDisableTiming));
   }
   CU(e, cudaEventRecord(e->ev_start, s));          // work already queued on the caller's stream comes first
   CU(e, cudaStreamWaitEvent(e->copy_in, e->ev_start, 0));
   CU(e, cudaStreamWaitEvent(e->copy_out, e->ev_start, 0));
+  static const bool no_slices = getenv("EMD_DISABLE_SLICED_IO") != nullptr;   // A/B switch: the two-chunk pipeline below
+  const bool sliceable = !no_slices && !e->profile && !e->keep && e->steps.size() >= 3 && e->steps.front().in.t == e->t_input &&
+                         e->steps.back().out.t == e->t_output && e->steps.back().in.t != e->t_input;
+  if (sliceable && n >= 16) {
+    // passes of up to max_batch crops (balanced, so that no pass is a small remainder)
+    const int npass = (n + e->max_batch - 1) / e->max_batch, pb = (n + npass - 1) / npass;
+    for (int c0 = 0, ip = 0; c0 < n; c0 += pb, ++ip) {
+      const int nb = std::min(pb, n - c0);
+      if ((rc = run_network_sliced(e, in_dev ? nullptr : crops + c0 * per, out_dev ? nullptr : out + c0 * per,
+                                   in_dev ? crops + c0 * per : e->d_stage_in, out_dev ? out + c0 * per : e->d_stage_out, nb, mode, s,
+                                   ip == 0)))
+        return rc;
+    }
+    CU(e, cudaStreamSynchronize(s));
+    if (!out_dev) CU(e, cudaStreamSynchronize(e->copy_out));
+    return EMD_OK;
+  }
   for (int i = 0; i < nchunks; ++i) {
     const int c0 = i * ch, nb = std::min(ch, n - c0), slot = i % nslots;
     const float* d_in = crops + c0 * per;
