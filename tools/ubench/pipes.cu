@@ -58,6 +58,26 @@ __global__ void __launch_bounds__(512) k(float* out, long long* cycles, int iter
           if (i & 4) asm volatile("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(a[i]) : "h"(xh), "h"(wh));
           else asm volatile("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(a[i]) : "h"(xl), "h"(wl));
         }
+      } else if (OP == 9 || OP == 10 || OP == 11) {  // mixes: 4 FFMA2 + 4 of {FHFMA (9), LOP3 (10), IMAD.U32 shift (11)}
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          unsigned long long x = ((unsigned long long)__float_as_uint(a[i + 1]) << 32) | __float_as_uint(a[i]);
+          unsigned long long w = ((unsigned long long)__float_as_uint(w1) << 32) | __float_as_uint(w0);
+          unsigned long long c = ((unsigned long long)__float_as_uint(b[i + 1]) << 32) | __float_as_uint(b[i]);
+          unsigned long long d;
+          asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(x), "l"(w), "l"(c));
+          a[i] = __uint_as_float((uint32_t)d); a[i + 1] = __uint_as_float((uint32_t)(d >> 32));
+          if (OP == 9) {
+            unsigned short xl, xh, wl, wh;
+            asm("mov.b32 {%0,%1}, %2;" : "=h"(xl), "=h"(xh) : "r"(u[i]));
+            asm("mov.b32 {%0,%1}, %2;" : "=h"(wl), "=h"(wh) : "r"(u[i + 1]));
+            asm volatile("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(b[i]) : "h"(xl), "h"(wh));
+          } else if (OP == 10) {
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[i]) : "r"(u[i + 1]), "r"(0xffff0000u));
+          } else {
+            asm volatile("mul.lo.u32 %0, %1, 65536;" : "=r"(u[i]) : "r"(u[i + 1]));
+          }
+        }
       } else if (OP == 6) {  // HFMA2 fp16
 #pragma unroll
         for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(u[i]) : "r"(__float_as_uint(w0)), "r"(__float_as_uint(b[i])));
@@ -95,6 +115,9 @@ int main() {
   run<1>("FFMA2", 32);
   run<7>("FHFMA.BF16", 64);
   run<8>("FHFMA.BF16 l/h", 64);
+  run<9>("4FFMA2+4FHFMA", 64);
+  run<10>("4FFMA2+4LOP3", 64);
+  run<11>("4FFMA2+4IMAD", 64);
   run<2>("HFMA2.BF16", 64);
   run<6>("HFMA2.F16", 64);
   run<3>("SHL16+XOR", 64);
