@@ -65,22 +65,37 @@ __global__ void __launch_bounds__(kMathThreads + 32, 1) dw_tma_kernel(const __gr
     ptx::prefetch_tmap(&tmap);
   }
   __syncthreads();
-  const int my_items = (a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // Work split with CHUNK AFFINITY: worker = (CTA, math group); worker w keeps channel chunk w % nchunks for the whole launch
+  // and walks the tiles j, j + Wc, ... (j = its rank among the Wc workers of that chunk), so its 36 depthwise weights are
+  // loaded once instead of once per item and the per-item index arithmetic is one tile decode.
+  const int n_workers = 2 * (int)gridDim.x, n_tiles = a.items / a.nchunks;
+  auto worker = [&](int grp, int& c, int& j, int& wc, int& cnt) {
+    const int w = 2 * (int)blockIdx.x + grp;
+    c = w % a.nchunks; j = w / a.nchunks;
+    wc = (n_workers - c + a.nchunks - 1) / a.nchunks;
+    cnt = j < n_tiles ? (n_tiles - j + wc - 1) / wc : 0;
+  };
 
   if (threadIdx.x >= kMathThreads) {
     // ---------------- producer ----------------
     if (threadIdx.x == kMathThreads) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int k = 0, item = blockIdx.x; k < my_items; ++k, item += gridDim.x) {
-        const int tile = item / a.nchunks, c = item - tile * a.nchunks;
-        const int n_img = tile / a.tiles_per_img;
-        const int rem = tile - n_img * a.tiles_per_img;
-        const int by = rem / a.tiles_x, bx = rem - by * a.tiles_x;
-        ptx::mbar_wait(bar_empty + 8u * s, ph ^ 1u);
-        ptx::mbar_arrive_expect_tx(bar_full + 8u * s, kStageBytes);
-        ptx::tma_load_4d(base + (uint32_t)s * kStageBytes, &tmap, c * kChunk, bx * kTW - 1, by * kTH - 1, n_img, bar_full + 8u * s);
-        if (++s == kStages) { s = 0; ph ^= 1u; }
+      int c[2], j[2], wc[2], cnt[2];
+      worker(0, c[0], j[0], wc[0], cnt[0]);
+      worker(1, c[1], j[1], wc[1], cnt[1]);
+      const int rounds = cnt[0] > cnt[1] ? cnt[0] : cnt[1];
+      for (int k = 0; k < rounds; ++k) {
+        for (int g = 0; g < 2; ++g) {
+          if (k >= cnt[g]) continue;
+          const int tile = j[g] + k * wc[g];
+          const int n_img = tile / a.tiles_per_img;
+          const int rem = tile - n_img * a.tiles_per_img;
+          const int by = rem / a.tiles_x, bx = rem - by * a.tiles_x;
+          const int q = g + 2 * k, s = q % kStages;          // group g owns the stages of its own parity (kStages is even)
+          const uint32_t ph = (uint32_t)((q / kStages) & 1);
+          ptx::mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+          ptx::mbar_arrive_expect_tx(bar_full + 8u * s, kStageBytes);
+          ptx::tma_load_4d(base + (uint32_t)s * kStageBytes, &tmap, c[g] * kChunk, bx * kTW - 1, by * kTH - 1, n_img, bar_full + 8u * s);
+        }
       }
     }
     return;
@@ -89,27 +104,24 @@ __global__ void __launch_bounds__(kMathThreads + 32, 1) dw_tma_kernel(const __gr
   // ---------------- math warps ----------------
   const int grp = threadIdx.x >> 8, tg = threadIdx.x & 255, lane = threadIdx.x & 31;
   const int cq = tg & 15, col = tg >> 4;
-  int cur_c = -1;
+  int c, j0, wc, cnt;
+  worker(grp, c, j0, wc, cnt);
+  const int ch = c * kChunk + cq * 4;
+  const bool ch_ok = ch < p.in.C;
   float2 w[9][2];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {   // this thread's 9 x 4 depthwise weights
+    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ch_ok && cnt > 0) w0 = __ldg(reinterpret_cast<const float4*>(p.w + t * p.in.C + ch));
+    w[t][0] = make_float2(w0.x, w0.y); w[t][1] = make_float2(w0.z, w0.w);
+  }
   int s = grp % kStages;
   uint32_t ph = (uint32_t)((grp / kStages) & 1);
-  for (int k = grp; k < my_items; k += 2) {
-    const int item = blockIdx.x + k * gridDim.x;
-    const int tile = (int)fdiv((uint32_t)item, a.d_chunks), c = item - tile * a.nchunks;
+  for (int k = 0; k < cnt; ++k) {
+    const int tile = j0 + k * wc;
     const int n_img = (int)fdiv((uint32_t)tile, a.d_tpi);
     const int rem = tile - n_img * a.tiles_per_img;
     const int by = (int)fdiv((uint32_t)rem, a.d_tx), bx = rem - by * a.tiles_x;
-    const int ch = c * kChunk + cq * 4;
-    const bool ch_ok = ch < p.in.C;
-    if (c != cur_c) {  // this thread's 9 x 4 depthwise weights for the chunk
-      cur_c = c;
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ch_ok) w0 = __ldg(reinterpret_cast<const float4*>(p.w + t * p.in.C + ch));
-        w[t][0] = make_float2(w0.x, w0.y); w[t][1] = make_float2(w0.z, w0.w);
-      }
-    }
     ptx::mbar_wait(bar_full + 8u * s, ph);
     const uint8_t* hb = smem + (size_t)s * kStageBytes + col * (kChunk * 2) + cq * 8;
     float2 win[3][3][2];
