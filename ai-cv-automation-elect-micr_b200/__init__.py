@@ -6,3 +6,4 @@ from .engine import Engine  # noqa: F401
 from . import weights  # noqa: F401
 from . import sharding  # noqa: F401
 from . import tfckpt  # noqa: F401
+from . import micrograph_io  # noqa: F401
