@@ -186,7 +186,9 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
                  bar_rfull = bar_tempty + 16u;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 * kMaxStages + 4 + kMaxRing);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler can then prove the role branches warp-uniform and keep the MMA issuer's
+  // descriptors in uniform registers (otherwise every tcgen05.mma sits in an ELECT / 7x R2UR waterfall loop)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   constexpr int kEpiWarps = epi_warps(kDw), kEpiThreads = kEpiWarps * 32, kBaseThreads = base_threads(kDw);
   constexpr int kMmaWarp = kEpiWarps, kProdWarp = kEpiWarps + 1;
   // pair mode: the cluster (not the CTA) walks the item list; an item covers M tiles 2m and 2m+1 (one per CTA of the pair)
@@ -352,7 +354,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
         mbar_wait(bar_afull + 8u * sa, ra.phase);
         if (kDw) mbar_wait(bar_bfull + 8u * sb, rb.phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_lo = a_lo0 + (uint32_t)sa * (kAStageBytes >> 4), b_lo = b_lo0 + (uint32_t)sb * b_step;
           const uint32_t accum = kb != 0 ? 1u : 0u;
           if (c != a.nchunks - 1 || last_ksteps == 4) umma_kblock<kPair, 4>(d_tmem, a_lo, b_lo, idesc, accum);

@@ -248,6 +248,22 @@ def test_denoiser_restores_tf_checkpoint_directory(emd, setup, tmp_path):
     assert np.array_equal(a.denoise_crops(setup["crops"]), b.denoise_crops(setup["crops"]))
 
 
+def test_denoise_files_matches_in_memory_denoise(emd, setup, tmp_path):
+    """Micrographs from disk (32-bit float TIFF) through the streaming front-end give exactly what Denoiser.denoise gives."""
+    io = emd.micrograph_io
+    d = emd.Denoiser(checkpoint_loc=setup["w1"], mode="bf16", cropsize=S, max_batch=4)
+    rng = np.random.default_rng(11)
+    imgs = [rng.random((S + 24 + 8 * k, S + 40)).astype(np.float32) for k in range(3)]
+    paths = []
+    for k, im in enumerate(imgs):
+        paths.append(str(tmp_path / f"m{k}.tif"))
+        io.write_tiff(paths[-1], im)
+    done = io.denoise_files(d, paths, str(tmp_path / "out"), overlap=8)
+    assert [k for k, _ in done] == [0, 1, 2]
+    for (k, dst), im in zip(done, imgs):
+        assert np.array_equal(io.read_tiff(dst), d.denoise(im, overlap=8).astype(np.float32))
+
+
 # ---- variant B: the graph of the deployed class file (machine_learning/denoiser.py:58-398) --------------------
 
 def test_variant_b_fp32_and_bf16(emd):
