@@ -80,7 +80,7 @@ final_umma_kernel(const __grid_constant__ FinalArgs a, const __grid_constant__ C
   const uint32_t bar_hfull = smem_u32(bars), bar_hempty = bar_hfull + 8u * kStages, bar_tfull = bar_hempty + 8u * kStages,
                  bar_tempty = bar_tfull + 16u;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform roles
 
   // weight operand: row = tap (rows 9..15 zero), 64 channels = eight 16-byte chunks, chunk j of row r at (j ^ (r & 7))
   for (int i = threadIdx.x; i < kNB * kC; i += kThreads) {
@@ -125,7 +125,7 @@ final_umma_kernel(const __grid_constant__ FinalArgs a, const __grid_constant__ C
       mbar_wait(bar_tempty + 8u * acc, (uint32_t)(((tcount >> 1) & 1) ^ 1));
       mbar_wait(bar_hfull + 8u * s, ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t a_lo = a_lo0 + (uint32_t)s * (kStageBytes >> 4);
         const uint32_t d = tmem_base + (uint32_t)(acc * 2 * kNB);
         umma_kblock<false, 4>(d, a_lo, b_lo, idesc, 0u);                               // halo rows 0..127

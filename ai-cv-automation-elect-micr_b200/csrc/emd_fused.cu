@@ -238,8 +238,8 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == kProdWarp) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer: the whole warp walks the (uniform) loops, one elected lane issues =====================
+    {
       const char* wbase = reinterpret_cast<const char*>(p.w16);
       Ring ra(0, SA), rb(0, SB), rh(0, kDw ? SH : 1);
       if constexpr (kDw) {
@@ -252,6 +252,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
         const char* b_src = nullptr;
         bool h_new = true, b_new = true;
         while (h_tile < total_tiles || b_tile < total_tiles) {
+          bool progress = false;
           if (h_tile < total_tiles) {
             if (h_new) {
               int mt, ntile, var;
@@ -259,9 +260,13 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
               tile_coords(a, mt, h_img, h_y0, h_x0);
               h_new = false;
             }
-            if (mbar_test(bar_hempty + 8u * rh.idx, rh.phase ^ 1u)) {
-              mbar_arrive_expect_tx(bar_hfull + 8u * rh.idx, kHaloBytes);
-              tma_load_4d(sH + (uint32_t)rh.idx * kHaloBytes, &tmap_in, h_c * kBK, h_x0 - 1, h_y0 - 1, h_img, bar_hfull + 8u * rh.idx);
+            if (__all_sync(0xffffffffu, mbar_test(bar_hempty + 8u * rh.idx, rh.phase ^ 1u))) {
+              if (elect_one()) {
+                mbar_arrive_expect_tx(bar_hfull + 8u * rh.idx, kHaloBytes);
+                tma_load_4d(sH + (uint32_t)rh.idx * kHaloBytes, &tmap_in, h_c * kBK, h_x0 - 1, h_y0 - 1, h_img, bar_hfull + 8u * rh.idx);
+              }
+              __syncwarp();
+              progress = true;
               rh.advance(1);
               if (++h_c == a.nchunks) { h_c = 0; h_tile += step; h_new = true; }
             }
@@ -274,13 +279,23 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
               b_src = wbase + (size_t)a.nt.rows_before[ntile] * a.w_kblocks * 128 + (size_t)(a.v_wrow[0][0] * a.nchunks) * b_bytes;
               b_new = false;
             }
-            if (mbar_test(bar_bempty + 8u * rb.idx, rb.phase ^ 1u)) {
-              mbar_arrive_expect_tx(bar_bfull + 8u * rb.idx, b_bytes);
-              bulk_g2s(sB + (uint32_t)rb.idx * a.b_stage_bytes, b_src, b_bytes, bar_bfull + 8u * rb.idx);
+            if (__all_sync(0xffffffffu, mbar_test(bar_bempty + 8u * rb.idx, rb.phase ^ 1u))) {
+              if (elect_one()) {
+                mbar_arrive_expect_tx(bar_bfull + 8u * rb.idx, b_bytes);
+                bulk_g2s(sB + (uint32_t)rb.idx * a.b_stage_bytes, b_src, b_bytes, bar_bfull + 8u * rb.idx);
+              }
+              __syncwarp();
+              progress = true;
               b_src += b_bytes;
               rb.advance(1);
               if (++b_c == a.nchunks) { b_c = 0; b_tile += step; b_new = true; }
             }
+          }
+          // neither slot is free: sleep on a barrier (hardware-suspended, bounded) instead of spinning -- the producer shares its
+          // scheduler with math warps that need every issue slot
+          if (!progress) {
+            if (h_tile < total_tiles) mbar_try_wait_ns(bar_hempty + 8u * rh.idx, rh.phase ^ 1u, 400u);
+            else mbar_try_wait_ns(bar_bempty + 8u * rb.idx, rb.phase ^ 1u, 400u);
           }
         }
       }
@@ -295,7 +310,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
         tile_coords(a, mt, n_img, y0, x0);
         {
           const int xb = x0 * p.istride, yb = y0 * p.istride;
-          if (a.b_res && tile == first) {   // first tile of this CTA: bring in every weight block, once
+          if (a.b_res && tile == first && elect_one()) {   // first tile of this CTA: bring in every weight block, once
             mbar_arrive_expect_tx(bar_bfull, bytes * (uint32_t)(ntaps * a.nchunks));
             for (int t = 0; t < ntaps; ++t)
               for (int c = 0; c < a.nchunks; ++c)
@@ -307,19 +322,22 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
             for (int c = 0; c < a.nchunks; ++c) {
               mbar_wait(bar_aempty + 8u * ra.idx, ra.phase ^ 1u);
               const uint32_t bar = bar_afull + 8u * ra.idx;
-              if constexpr (kPair) {
-                // both CTAs' copies complete on the LEADER's full barrier; each CTA brings its own A tile and its half of B's rows
-                // (the weight box always has maxrows/2 rows; for a narrower last N tile the surplus rows are never read)
-                if (crank == 0) mbar_arrive_expect_tx(bar, 2u * ((uint32_t)(a.nt.maxrows >> 1) * 128u + (uint32_t)kAStageBytes));
-                tma_load_4d_2sm(sA + (uint32_t)ra.idx * kAStageBytes, &tmap_in, c * kBK, xt, yt, n_img, bar);
-                const int half = a.nt.rows[ntile] >> 1;
-                tma_load_2d_2sm(sB + (uint32_t)ra.idx * a.b_stage_bytes, &tmap_w, 0,
-                                (a.b_row0[ntile] + (a.v_wrow[var][t] * a.nchunks + c) * a.nt.rows[ntile] + (int)crank * half) >> 2, bar);
-              } else {
-                mbar_arrive_expect_tx(bar, (a.b_res ? 0u : bytes) + (uint32_t)kAStageBytes);
-                tma_load_4d(sA + (uint32_t)ra.idx * kAStageBytes, &tmap_in, c * kBK, xt, yt, n_img, bar);
-                if (!a.b_res) bulk_g2s(sB + (uint32_t)ra.idx * a.b_stage_bytes, wsrc, bytes, bar);
+              if (elect_one()) {
+                if constexpr (kPair) {
+                  // both CTAs' copies complete on the LEADER's full barrier; each CTA brings its own A tile and its half of B's rows
+                  // (the weight box always has maxrows/2 rows; for a narrower last N tile the surplus rows are never read)
+                  if (crank == 0) mbar_arrive_expect_tx(bar, 2u * ((uint32_t)(a.nt.maxrows >> 1) * 128u + (uint32_t)kAStageBytes));
+                  tma_load_4d_2sm(sA + (uint32_t)ra.idx * kAStageBytes, &tmap_in, c * kBK, xt, yt, n_img, bar);
+                  const int half = a.nt.rows[ntile] >> 1;
+                  tma_load_2d_2sm(sB + (uint32_t)ra.idx * a.b_stage_bytes, &tmap_w, 0,
+                                  (a.b_row0[ntile] + (a.v_wrow[var][t] * a.nchunks + c) * a.nt.rows[ntile] + (int)crank * half) >> 2, bar);
+                } else {
+                  mbar_arrive_expect_tx(bar, (a.b_res ? 0u : bytes) + (uint32_t)kAStageBytes);
+                  tma_load_4d(sA + (uint32_t)ra.idx * kAStageBytes, &tmap_in, c * kBK, xt, yt, n_img, bar);
+                  if (!a.b_res) bulk_g2s(sB + (uint32_t)ra.idx * a.b_stage_bytes, wsrc, bytes, bar);
+                }
               }
+              __syncwarp();
               wsrc += bytes;
               ra.advance(1);
             }

@@ -124,6 +124,17 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
       "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+// one potentially-blocking probe: the thread may be suspended by the hardware for up to ~ns nanoseconds
+__device__ __forceinline__ bool mbar_try_wait_ns(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // 4-D tiled TMA load (c, x, y, n); out-of-range coordinates are zero-filled = TF SAME padding

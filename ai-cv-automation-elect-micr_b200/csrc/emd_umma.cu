@@ -51,6 +51,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {   // one lane of a converged warp (elect.sync)
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -201,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                  bar_tempty = bar_tfull + 16u;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform roles (emd_fused.cu)
   const int total_tiles = a.m_tiles * a.nt.nt;
   const int kblocks = p.ntaps * a.nchunks;
 
@@ -320,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         const uint32_t ph = (uint32_t)((it / S) & 1);
         mbar_wait(bar_full + 8u * s, ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const int kvalid = min(kBK, p.Cin - c * kBK);
           const int ksteps = (kvalid + 15) >> 4;
           const uint64_t adesc = make_sdesc(sA + (uint32_t)s * kAStageBytes);
