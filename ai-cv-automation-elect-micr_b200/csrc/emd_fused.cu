@@ -431,28 +431,30 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(acc * a.acc_stride);
       const int nslabs = (n + 63) >> 6;
-      for (int j = 0; j < nslabs; ++j) {
+      // this warp converts the 32-column half `my_half` of every 64-column slab; the accumulator read of slab j+1 is in
+      // flight while slab j is converted and stored (the epilogue, not the MMA, paces the output-heavy layers)
+      constexpr int kVB = kDw ? 1 : 2;           // dw mode runs at 72 registers per thread: no room for a second buffer
+      uint32_t v[kVB][32];
+      const int cbase = my_half * 32;
+      if (!kDw && cbase < n) tmem_ld32(taddr + (uint32_t)cbase, v[0]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j >= nslabs) break;
         const int buf = rq.idx;
         uint8_t* srow = g_stage + (size_t)buf * kSlabBytes + row_off;
+        const int c0 = j * 64 + cbase;           // column within the N tile
+        if (kDw && c0 < n) tmem_ld32(taddr + (uint32_t)c0, v[0]);
+        tmem_ld_wait();
+        if (!kDw && j + 1 < nslabs && c0 + 64 < n) tmem_ld32(taddr + (uint32_t)(c0 + 64), v[(j + 1) % kVB]);
+        if (j == nslabs - 1) {                   // this warp's last read of the accumulator is done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if constexpr (kPair) mbar_arrive_leader(bar_tempty + 8u * acc); else mbar_arrive(bar_tempty + 8u * acc); }
+        }
         if (kRes) mbar_wait(bar_rfull + 8u * buf, rq.phase);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c0 = j * 64 + h * 32;        // column within the N tile
-          const bool mine = kEpiWarps == 4 || h == my_half;
-          uint32_t v[32];
-          if (mine && c0 < n) {
-            tmem_ld32(taddr + (uint32_t)c0, v);
-            tmem_ld_wait();
-          }
-          if (j == nslabs - 1 && h == 1) {       // this warp's last read of the accumulator is done: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) { if constexpr (kPair) mbar_arrive_leader(bar_tempty + 8u * acc); else mbar_arrive(bar_tempty + 8u * acc); }
-          }
-          if (mine && c0 < n) {
-            if (p.relu6) epi_half<T, kRes, true>(v, s_scale + n0 + c0, s_shift + n0 + c0, srow, h, rsw);
-            else epi_half<T, kRes, false>(v, s_scale + n0 + c0, s_shift + n0 + c0, srow, h, rsw);
-          }
+        if (c0 < n) {
+          if (p.relu6) epi_half<T, kRes, true>(v[j % kVB], s_scale + n0 + c0, s_shift + n0 + c0, srow, my_half, rsw);
+          else epi_half<T, kRes, false>(v[j % kVB], s_scale + n0 + c0, s_shift + n0 + c0, srow, my_half, rsw);
         }
         fence_proxy_async();               // make this thread's slab writes visible to the TMA engine
         if (tid == 0) {                    // the slab the NEXT iteration writes must have been read out by its last store
