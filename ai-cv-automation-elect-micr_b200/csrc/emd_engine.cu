@@ -959,7 +959,7 @@ int emd_forward(emd_engine* e, const float* crops, int n, float* out, int mode, 
   static const bool no_slices = getenv("EMD_DISABLE_SLICED_IO") != nullptr;   // A/B switch: the two-chunk pipeline below
   const bool sliceable = !no_slices && !e->profile && !e->keep && e->steps.size() >= 3 && e->steps.front().in.t == e->t_input &&
                          e->steps.back().out.t == e->t_output && e->steps.back().in.t != e->t_input;
-  if (sliceable && n >= 16) {
+  if (sliceable && n >= 16 && e->max_batch >= 16) {
     // passes of up to max_batch crops (balanced, so that no pass is a small remainder)
     const int npass = (n + e->max_batch - 1) / e->max_batch, pb = (n + npass - 1) / npass;
     for (int c0 = 0, ip = 0; c0 < n; c0 += pb, ++ip) {
