@@ -684,7 +684,22 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
   const size_t per = (size_t)e->S * e->S;
   static const int k_env = getenv("EMD_IO_SLICES") ? atoi(getenv("EMD_IO_SLICES")) : 0;   // tuning switch
   const int K = k_env > 0 && k_env <= emd_engine::kSlices ? k_env : emd_engine::kSlices;
-  const int qs = (n + K - 1) / K, last = (int)e->steps.size() - 1;
+  const int last = (int)e->steps.size() - 1;
+  // slice boundaries: what stays exposed is the FIRST upload and the LAST download, so those two slices are one crop each
+  // and the rest of the batch is split evenly
+  int in_b[emd_engine::kSlices + 1], out_b[emd_engine::kSlices + 1];
+  int nin = 0, nout = 0;
+  {
+    const int k = std::min(K, n), rest = n - 1, parts = std::max(k - 1, 1);
+    in_b[nin++] = 0;
+    if (k > 1) in_b[nin++] = 1;
+    for (int i = 1; i <= parts && k > 1; ++i) { const int b = 1 + (int)((long long)rest * i / parts); if (b > in_b[nin - 1]) in_b[nin++] = b; }
+    if (k <= 1) in_b[nin++] = n;
+    out_b[nout++] = 0;
+    for (int i = 1; i <= parts && k > 1; ++i) { const int b = (int)((long long)rest * i / parts); if (b > out_b[nout - 1]) out_b[nout++] = b; }
+    out_b[nout++] = n;
+  }
+  const int n_in = nin - 1, n_out = nout - 1;   // number of slices each way (<= kSlices)
   int head = 1;         // the steps of the first layer (its depthwise and pointwise halves)
   while (head < last && e->steps[head].layer == e->steps[0].layer) ++head;
   int in_free_at = head;   // the step after which the staging copy of the crops is dead (a fused depthwise reads at the next step)
@@ -700,13 +715,13 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
   int rc;
   if (h_in) {
     if (!first_pass) CU(e, cudaStreamWaitEvent(e->copy_in, e->ev_in_free, 0));      // the pass before has read the staging buffer
-    for (int q = 0; q * qs < n; ++q) {
-      const int b0 = q * qs, nb = std::min(qs, n - b0);
+    for (int q = 0; q < n_in; ++q) {
+      const int b0 = in_b[q], nb = in_b[q + 1] - b0;
       CU(e, cudaMemcpyAsync(const_cast<float*>(d_in) + b0 * per, h_in + b0 * per, nb * per * 4, cudaMemcpyHostToDevice, e->copy_in));
       CU(e, cudaEventRecord(e->ev_sl_in[q], e->copy_in));
     }
-    for (int q = 0; q * qs < n; ++q) {
-      const int b0 = q * qs, nb = std::min(qs, n - b0);
+    for (int q = 0; q < n_in; ++q) {
+      const int b0 = in_b[q], nb = in_b[q + 1] - b0;
       CU(e, cudaStreamWaitEvent(s, e->ev_sl_in[q], 0));
       for (int i = 0; i < head; ++i)
         if ((rc = step(i, b0, nb))) return rc;
@@ -721,8 +736,8 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
   }
   if (h_out) {
     if (!first_pass) CU(e, cudaStreamWaitEvent(s, e->ev_out_free, 0));              // the D2H copies of the pass before have drained
-    for (int q = 0; q * qs < n; ++q) {
-      const int b0 = q * qs, nb = std::min(qs, n - b0);
+    for (int q = 0; q < n_out; ++q) {
+      const int b0 = out_b[q], nb = out_b[q + 1] - b0;
       if ((rc = step(last, b0, nb))) return rc;
       CU(e, cudaEventRecord(e->ev_sl_fin[q], s));
       CU(e, cudaStreamWaitEvent(e->copy_out, e->ev_sl_fin[q], 0));
