@@ -290,7 +290,7 @@ def main():
         top = sorted(info, key=lambda i: -i[1])[:8]
         roof["top_steps_ms"] = {i[0]: round(i[1], 3) for i in top}
         out["roofline"] = roof
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU leg is reported at N=1 only (the other ranks would wait for it)
             n_pass = 12   # ~10 s of CPU work on the box's host cores
             v, cores = time_cpu_oracle(n_pass, S)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
