@@ -7,3 +7,4 @@ from . import weights  # noqa: F401
 from . import sharding  # noqa: F401
 from . import tfckpt  # noqa: F401
 from . import micrograph_io  # noqa: F401
+from . import quality  # noqa: F401

@@ -33,6 +33,7 @@ SIGNATURES = {
     "emd_gather_crops": (_I, [_P, _P, _I, _I, _IP, _IP, _I, _I, _I, _P, _P]),
     "emd_stitch": (_I, [_P, _P, _IP, _IP, _I, _I, _I, _I, _I, _I, _P, _P]),
     "emd_denoise_image": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "emd_quality": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "emd_set_keep_activations": (_I, [_P, _I]),
     "emd_get_activation": (_I, [_P, C.c_char_p, _P, _SZ, _IP]),
     "emd_run_layer": (_I, [_P, C.c_char_p, _P, _P, _I, _P, _SZ, _I, _IP]),

@@ -86,6 +86,7 @@ struct emd_engine {
   cudaEvent_t ev_sl_in[kSlices] = {}, ev_sl_fin[kSlices] = {}, ev_in_free = nullptr, ev_out_free = nullptr;
   // whole-image pipeline buffers (grown on demand)
   void* d_img_raw = nullptr; size_t img_raw_bytes = 0;
+  char *d_q_a = nullptr, *d_q_b = nullptr, *d_q_partial = nullptr; size_t q_a_bytes = 0, q_b_bytes = 0, q_partial_bytes = 0;   // emd_quality
   float* d_img = nullptr; size_t img_bytes = 0;
   float *d_crops = nullptr, *d_tiles = nullptr; size_t crops_bytes = 0, tiles_bytes = 0;
   double* d_sout = nullptr; size_t sout_bytes = 0;
@@ -883,7 +884,7 @@ int emd_destroy(emd_engine* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (void* p : e->w16_allocs) cudaFree(p);
-  for (void* p : {(void*)e->arena, (void*)e->d_blob, (void*)e->d_stage_in, (void*)e->d_stage_out, e->d_img_raw,
+  for (void* p : {(void*)e->arena, (void*)e->d_blob, (void*)e->d_stage_in, (void*)e->d_stage_out, e->d_img_raw, (void*)e->d_q_a, (void*)e->d_q_b, (void*)e->d_q_partial,
                   (void*)e->d_img, (void*)e->d_crops, (void*)e->d_tiles, (void*)e->d_sout, (void*)e->d_minmax,
                   e->d_partial, (void*)e->d_origins})
     if (p) cudaFree(p);
@@ -1125,6 +1126,36 @@ int emd_stitch(emd_engine* e, const float* tiles, const int* ys, const int* xs, 
     CU(e, cudaMemcpyAsync(out, d_dst, nout, cudaMemcpyDeviceToHost, s));
     CU(e, cudaStreamSynchronize(s));
   }
+  return EMD_OK;
+}
+
+int emd_quality(emd_engine* e, const float* a, const float* b, int n, int H, int W, double* out, void* stream) {
+  if (!e || !a || !b || !out || n < 0) return EMD_EINVAL;
+  if (H < 11 || W < 11) return fail(e, EMD_EINVAL, "images of %dx%d are smaller than the 11x11 SSIM window", H, W);
+  if (n == 0) return EMD_OK;
+  CU(e, cudaSetDevice(e->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  const size_t bytes = (size_t)n * H * W * sizeof(float);
+  int rc;
+  const float *da = a, *db = b;
+  if (!is_device_ptr(a)) {
+    if ((rc = grow(e, &e->d_q_a, &e->q_a_bytes, bytes))) return rc;
+    CU(e, cudaMemcpyAsync(e->d_q_a, a, bytes, cudaMemcpyHostToDevice, s));
+    da = reinterpret_cast<const float*>(e->d_q_a);
+  }
+  if (!is_device_ptr(b)) {
+    if ((rc = grow(e, &e->d_q_b, &e->q_b_bytes, bytes))) return rc;
+    CU(e, cudaMemcpyAsync(e->d_q_b, b, bytes, cudaMemcpyHostToDevice, s));
+    db = reinterpret_cast<const float*>(e->d_q_b);
+  }
+  const size_t pbytes = quality_partial_bytes(n, H, W) + (size_t)n * 3 * sizeof(double);
+  if ((rc = grow(e, &e->d_q_partial, &e->q_partial_bytes, pbytes))) return rc;
+  double* d_partial = reinterpret_cast<double*>(e->d_q_partial);
+  double* d_out = d_partial + quality_partial_bytes(n, H, W) / sizeof(double);
+  CU(e, launch_quality(da, db, n, H, W, d_partial, d_out, s));
+  e->launches += 2;
+  CU(e, cudaMemcpyAsync(out, d_out, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(e, cudaStreamSynchronize(s));
   return EMD_OK;
 }
 

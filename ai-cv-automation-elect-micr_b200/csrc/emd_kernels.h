@@ -133,6 +133,10 @@ cudaError_t launch_conv_fused_multi(const ConvParams* ps, int nvar, int et, int 
 void fused_set_enabled(bool on);
 void fused_set_pair(bool on);    // 2-CTA (cta_group::2) GEMM for wide N tiles; default on
 
+// emd_quality.cu: MSE / Huberised loss / SSIM of image pairs (d_out = 3 doubles per pair, d_partial = quality_partial_bytes)
+size_t quality_partial_bytes(int n, int H, int W);
+cudaError_t launch_quality(const float* a, const float* b, int n, int H, int W, double* d_partial, double* d_out, cudaStream_t s);
+
 // emd_kernels_wrap.cu: whole-image wrapper kernels
 cudaError_t launch_minmax(const void* img, int in_f64, size_t n, double* d_minmax /*[2]*/, void* d_partial,
                           cudaStream_t s);

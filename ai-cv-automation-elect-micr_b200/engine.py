@@ -139,6 +139,21 @@ class Engine:
                                         _ptr(out), None), "emd_stitch")
         return out
 
+    def quality(self, a, b):
+        """MSE, the trainer's Huberised loss and mean SSIM (tf_ssim) between image pairs: a, b [n,H,W] (or [H,W]) float32,
+        numpy or torch (host / CUDA) -> float64 array [n,3] (emd_quality)."""
+        if isinstance(a, np.ndarray):
+            a = np.ascontiguousarray(a, np.float32)
+        if isinstance(b, np.ndarray):
+            b = np.ascontiguousarray(b, np.float32)
+        if tuple(a.shape) != tuple(b.shape) or len(a.shape) not in (2, 3):
+            raise ValueError(f"quality: shapes {tuple(a.shape)} and {tuple(b.shape)}")
+        n = 1 if len(a.shape) == 2 else int(a.shape[0])
+        H, W = int(a.shape[-2]), int(a.shape[-1])
+        out = np.empty((n, 3), np.float64)
+        self._check(self.lib.emd_quality(self.h, _ptr(a), _ptr(b), n, H, W, _ptr(out), _stream_for(a, None)), "emd_quality")
+        return out
+
     def denoise_image(self, img, overlap=80, preprocess=True, postprocess=True, mode="bf16", out=None):
         """Whole micrograph in one call: normalise -> tile -> batched forward -> stitch (emd_denoise_image)."""
         is_np = isinstance(img, np.ndarray)

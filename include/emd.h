@@ -102,6 +102,13 @@ int emd_stitch(emd_engine* e, const float* tiles, const int* ys, const int* xs, 
 int emd_denoise_image(emd_engine* e, const void* img, int H, int W, int overlap, int flags,
                       int mode, double* out, void* stream);
 
+/* Image-quality metrics of the reference's training / evaluation code (misc_py/denoiser-multi-gpu.py) between n pairs of
+ * [H,W] f32 images a[i], b[i] (host or device; H, W >= 11): out[3*i + 0] = mean squared error (DMG:772),
+ * out[3*i + 1] = the trainer's Huberised loss of it, mse < 0.001 ? 1000*mse : sqrt(1000*mse) (DMG:773),
+ * out[3*i + 2] = mean SSIM as tf_ssim computes it (DMG:142-167: 11x11 Gaussian window, sigma 1.5, VALID, K1 0.01, K2 0.03,
+ * L 1).  out = 3*n doubles in HOST memory. */
+int emd_quality(emd_engine* e, const float* a, const float* b, int n, int H, int W, double* out, void* stream);
+
 /* ---- parity / measurement hooks (no reference counterpart; used by tests and bench.py) ---- */
 
 /* keep != 0: every activation gets its own buffer (no reuse) so emd_get_activation works */
