@@ -164,8 +164,12 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / done, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "one 512x512 synthetic crop per step, batch 1, PyTorch-CPU restatement of the reference "
-                               "TF graph (TensorFlow is not installable here)", "crop": CROP, "batch": 1},
+        "config": {"workload": f"batch {BATCH} of {CROP}x{CROP} synthetic crops per GPU per step through the atrous Xception "
+                               f"denoiser (variant A, random-init weights), BASELINE.json configs[1]",
+                   "batch_per_gpu": BATCH, "crop": CROP, "mode": "f32",
+                   "sample_per_step": "1 of the batch's crops per timed step (the reference runs one sess.run per crop, "
+                                      "DEN:646-647, so crops/s does not depend on the batch); PyTorch-CPU restatement of the "
+                                      "reference TF graph, TensorFlow is not installable here"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
