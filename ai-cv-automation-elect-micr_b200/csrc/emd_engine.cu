@@ -95,7 +95,7 @@ struct emd_engine {
   std::vector<cudaEvent_t> events;
   // CUDA graphs of whole passes for small batches
   bool use_graphs = true;
-  int graph_max_n = 8;
+  int graph_max_n = 32;
   std::map<int, GraphSlot> graphs;
   float *g_in = nullptr, *g_out = nullptr;
   long long graph_replays = 0;
@@ -839,6 +839,8 @@ int emd_create(emd_engine** out, int device, int cropsize, int variant, int max_
   e->use_umma = !(env && env[0] == '1');
   env = getenv("EMD_DISABLE_GRAPH");
   e->use_graphs = !(env && env[0] == '1');
+  env = getenv("EMD_GRAPH_MAX_N");   // tuning switch: largest batch replayed from a CUDA graph
+  if (env && atoi(env) > 0) e->graph_max_n = atoi(env);
   env = getenv("EMD_DISABLE_TMA");
   umma_set_tma(!(env && env[0] == '1'));
   env = getenv("EMD_DISABLE_PAIR");

@@ -121,7 +121,7 @@ int emd_run_layer(emd_engine* e, const char* name, const float* in, const float*
 /* number of kernels this engine has launched since creation; of those, tcgen05 (UMMA) kernels */
 long long emd_kernel_launches(const emd_engine* e);
 long long emd_tensor_core_launches(const emd_engine* e);
-/* passes replayed from a captured CUDA graph (batches <= 8 from their third pass on; EMD_DISABLE_GRAPH=1 turns it off) */
+/* passes replayed from a captured CUDA graph (batches <= 32 from their third pass on; EMD_DISABLE_GRAPH=1 turns it off, EMD_GRAPH_MAX_N changes the limit) */
 long long emd_graph_replays(const emd_engine* e);
 /* on = 0: the 16-bit modes run their GEMM-class layers on the CUDA-core kernel with the same
  * 16-bit operand values (A/B check of the tcgen05 kernel); default on */
