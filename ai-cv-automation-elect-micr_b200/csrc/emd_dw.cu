@@ -53,6 +53,7 @@ template <typename T, bool kReduce>
 __global__ void __launch_bounds__(kMathThreads + 32, 1) dw_tma_kernel(const __grid_constant__ DwTmaArgs a,
                                                                       const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ uint8_t smem_raw[];
+  ptx::griddep_launch();
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 127u) & ~127u;
   uint8_t* smem = smem_raw + (base - raw);
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(kMathThreads + 32, 1) dw_tma_kernel(const __gr
     ptx::prefetch_tmap(&tmap);
   }
   __syncthreads();
+  ptx::griddep_wait();   // the layer before has finished (emd_tma.h)
   // Work split with CHUNK AFFINITY: worker = (CTA, math group); worker w keeps channel chunk w % nchunks for the whole launch
   // and walks the tiles j, j + Wc, ... (j = its rank among the Wc workers of that chunk), so its 36 depthwise weights are
   // loaded once instead of once per item and the per-item index arithmetic is one tile decode.
@@ -286,8 +288,16 @@ static cudaError_t launch_t(const DwTmaArgs& a, const CUtensorMap& tmap, int gri
     if (r != cudaSuccess) return r;
     attr_dev = dev;
   }
-  dw_tma_kernel<T, kReduce><<<grid, kMathThreads + 32, smem, s>>>(a, tmap);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)(kMathThreads + 32));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, dw_tma_kernel<T, kReduce>, a, tmap);
 }
 
 static cudaError_t launch_common(DwTmaArgs& a, int et, bool reduce, int num_sms, cudaStream_t s) {

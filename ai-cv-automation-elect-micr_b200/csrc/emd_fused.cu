@@ -165,6 +165,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
                   const __grid_constant__ OutMaps tmaps_out, const __grid_constant__ CUtensorMap tmap_res,
                   const __grid_constant__ CUtensorMap tmap_w) {
   extern __shared__ uint8_t smem_raw[];
+  griddep_launch();
   const ConvParams& p = a.p;
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
@@ -236,6 +237,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
   if constexpr (kPair) cluster_sync_all();      // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();                               // the layer before has finished: activations may be read and written from here on
 
   if (warp == kProdWarp) {
     // ===================== TMA producer: the whole warp walks the (uniform) loops, one elected lane issues =====================
@@ -565,20 +567,25 @@ cudaError_t launch_t(const FusedArgs& a, const CUtensorMap& tin, const OutMaps& 
     attr_dev = dev;
   }
   const int block = kDw ? base_threads(true) + kMathThreads : base_threads(false);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   if (kPair) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3((unsigned)block);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, fused_conv_kernel<T, kDw, kRes, kPair>, a, tin, tout, tres, tw);
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
   }
-  fused_conv_kernel<T, kDw, kRes, kPair><<<grid, block, smem, s>>>(a, tin, tout, tres, tw);
-  return cudaGetLastError();
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, fused_conv_kernel<T, kDw, kRes, kPair>, a, tin, tout, tres, tw);
 }
 
 }  // namespace

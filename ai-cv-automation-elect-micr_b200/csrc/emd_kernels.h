@@ -3,6 +3,7 @@
 // read/write a channel slice [coff, coff+C) of a wider tensor -- that is how concats are formed
 // without a copy, DMG:348-350 / 497-499 / 509-511).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -132,6 +133,12 @@ bool fused_multi_supported(const ConvParams* ps, int nvar, int et);
 cudaError_t launch_conv_fused_multi(const ConvParams* ps, int nvar, int et, int num_sms, cudaStream_t s);
 void fused_set_enabled(bool on);
 void fused_set_pair(bool on);    // 2-CTA (cta_group::2) GEMM for wide N tiles; default on
+
+// programmatic dependent launch for the kernels that carry griddepcontrol.wait (emd_fused.cu, emd_dw.cu); EMD_DISABLE_PDL=1 = A/B switch
+inline bool pdl_enabled() {
+  static const bool on = !(getenv("EMD_DISABLE_PDL") && getenv("EMD_DISABLE_PDL")[0] == '1');
+  return on;
+}
 
 // emd_quality.cu: MSE / Huberised loss / SSIM of image pairs (d_out = 3 doubles per pair, d_partial = quality_partial_bytes)
 size_t quality_partial_bytes(int n, int H, int W);

@@ -189,6 +189,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // ---- tcgen05 / TMEM ----
+// Programmatic dependent launch (a kernel launched with the programmatic-stream-serialization attribute may become resident
+// while the kernel before it in the stream is still running): `griddep_launch` lets the NEXT kernel's CTAs start taking free
+// SMs; `griddep_wait` blocks until the PREVIOUS kernel has completed and its writes are visible -- everything that reads or
+// writes activations comes after it, only the prologue (barriers, TMEM, tensor maps, constant weights) before.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // one lane of a converged warp (elect.sync): the form the compiler recognises as a single-thread region of a uniform warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
