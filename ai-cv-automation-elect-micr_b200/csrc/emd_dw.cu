@@ -185,6 +185,7 @@ template <typename T>
 __global__ void __launch_bounds__(kS2Groups* kS2GroupThreads + 32, 1) dw_s2_tma_kernel(const __grid_constant__ DwTmaArgs a,
                                                                                        const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ uint8_t smem_raw[];
+  ptx::griddep_launch();
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 127u) & ~127u;
   uint8_t* smem = smem_raw + (base - raw);
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(kS2Groups* kS2GroupThreads + 32, 1) dw_s2_tma_
     ptx::prefetch_tmap(&tmap);
   }
   __syncthreads();
+  ptx::griddep_wait();   // the layer before has finished (emd_tma.h)
   const int my_items = (a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (threadIdx.x >= kS2Groups * kS2GroupThreads) {
@@ -343,8 +345,16 @@ static cudaError_t launch_s2_t(const DwTmaArgs& a, const CUtensorMap& tmap, int 
     if (r != cudaSuccess) return r;
     attr_dev = dev;
   }
-  dw_s2_tma_kernel<T><<<grid, kS2Groups * kS2GroupThreads + 32, smem, s>>>(a, tmap);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)(kS2Groups * kS2GroupThreads + 32));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, dw_s2_tma_kernel<T>, a, tmap);
 }
 
 cudaError_t launch_dw_s2_tma(const DwParams& p, int et, int num_sms, cudaStream_t s) {

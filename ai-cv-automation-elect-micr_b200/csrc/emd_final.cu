@@ -73,6 +73,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
 final_umma_kernel(const __grid_constant__ FinalArgs a, const __grid_constant__ CUtensorMap tmap_in) {
   extern __shared__ uint8_t smem_raw[];
+  griddep_launch();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023u) & ~(uintptr_t)1023u);
   uint8_t* s_b = smem + (size_t)kStages * kStageBytes;                        // 16 rows x 128 B, swizzled (2 KB)
   float* s_g = reinterpret_cast<float*>(s_b + 2048);                          // [2][9][kGPitch]
@@ -100,6 +101,7 @@ final_umma_kernel(const __grid_constant__ FinalArgs a, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();               // the layer before has finished (emd_tma.h)
   const int first = blockIdx.x, step = gridDim.x;
 
   if (warp == kProdWarp) {
@@ -190,8 +192,16 @@ cudaError_t launch_t(const FinalArgs& a, const CUtensorMap& tmap, int grid, size
     if (r != cudaSuccess) return r;
     attr_dev = dev;
   }
-  final_umma_kernel<T><<<grid, kThreads, smem, s>>>(a, tmap);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, final_umma_kernel<T>, a, tmap);
 }
 
 }  // namespace
