@@ -82,6 +82,7 @@ struct emd_engine {
   cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of emd_forward with host buffers
   cudaEvent_t ev_in[2] = {}, ev_done[2] = {}, ev_out[2] = {}, ev_start = nullptr;
   int last_input_step = 0;                                // last step that reads the network input
+  int head_end = -1, tail_start = 1 << 30;                // half-batch phases of the host-buffer pass (plan_arena)
   static constexpr int kSlices = 8;                       // sliced first / last step of a pass (emd_forward, host buffers)
   cudaEvent_t ev_sl_in[kSlices] = {}, ev_sl_fin[kSlices] = {}, ev_in_free = nullptr, ev_out_free = nullptr;
   // whole-image pipeline buffers (grown on demand)
@@ -332,6 +333,22 @@ int plan_arena(emd_engine* e) {
     // while that step's output is being written, so the input must stay live (un-aliased) through the next step
     if (s.kind == SK_DW && i + 1 < (int)e->steps.size() && e->steps[i + 1].layer == s.layer)
       e->tensors[s.in.t].last = std::max(e->tensors[s.in.t].last, i + 1);
+  }
+  // Host-buffer passes (run_network_sliced) run the high-resolution head of the network (outputs >= S/2) and its
+  // full-resolution tail once per HALF of the batch, so that the second half's upload and the first half's download hide
+  // under the other half's compute.  Inside such a phase a late step of half 1 runs before an early step of half 2:
+  // tensors touched by a phase must not share memory with each other.
+  const int nsteps = (int)e->steps.size();
+  e->head_end = -1; e->tail_start = nsteps;
+  if (e->max_batch >= 16) {
+    for (int i = 0; i < nsteps && e->tensors[e->steps[i].out.t].H * 2 >= e->S; ++i) e->head_end = i;
+    for (int i = nsteps - 1; i >= 0 && e->tensors[e->steps[i].out.t].H >= e->S; --i) e->tail_start = i;
+    if (e->head_end < 0 || e->tail_start >= nsteps || e->head_end + 1 >= e->tail_start) { e->head_end = -1; e->tail_start = nsteps; }
+    for (Tensor& t : e->tensors) {
+      if (t.last < 0) continue;
+      if (t.first <= e->head_end) { t.first = 0; t.last = std::max(t.last, e->head_end); }
+      if (t.last >= e->tail_start) { t.first = std::min(t.first, e->tail_start); t.last = nsteps - 1; }
+    }
   }
   std::vector<int> order;
   for (int i = 0; i < (int)e->tensors.size(); ++i) {
@@ -674,38 +691,27 @@ int run_network_direct(emd_engine* e, const float* d_in, float* d_out, int n, in
   return EMD_OK;
 }
 
-// One pass over a large batch with HOST input and / or output: only the first step reads the crops and only the last one
-// writes the result, so those two run slice by slice -- the first step on slice q as soon as its H2D copy has landed, the
-// D2H copy of slice q as soon as the last step has written it -- and everything in between runs once on the whole batch.
-// Exposed copy time is one slice each way instead of one chunk, and the network keeps its full-batch efficiency.
+// One pass over a large batch with HOST input and / or output.  Only the first layer reads the crops and only the last one
+// writes the result, so those two run slice by slice -- the first on a slice as soon as its H2D copy has landed, the D2H
+// copy of a slice as soon as the last layer has written it.  Around them, the high-resolution head of the network and its
+// full-resolution tail (plan_arena: head_end / tail_start) run once per HALF of the batch, so the second half's upload
+// hides under the first half's head and the first half's download under the second half's tail; everything in between
+// runs once on the whole batch and keeps its full-batch efficiency.  What stays exposed is one crop's copy each way.
 // h_in / h_out null = that side is already on the device (d_in / d_out used as given).
 int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const float* d_in, float* d_out, int n, int mode,
                        cudaStream_t s, bool first_pass) {
   ExecCtx c{e, mode == EMD_MODE_FP32 ? ET_F32 : (mode == EMD_MODE_BF16 ? ET_BF16 : ET_F16), n, s, d_in, d_out, {}};
   const size_t per = (size_t)e->S * e->S;
-  static const int k_env = getenv("EMD_IO_SLICES") ? atoi(getenv("EMD_IO_SLICES")) : 0;   // tuning switch
+  static const int k_env = getenv("EMD_IO_SLICES") ? atoi(getenv("EMD_IO_SLICES")) : 0;   // tuning switches
+  static const bool no_halves = getenv("EMD_DISABLE_HALVES") != nullptr;
   const int K = k_env > 0 && k_env <= emd_engine::kSlices ? k_env : emd_engine::kSlices;
   const int last = (int)e->steps.size() - 1;
-  // slice boundaries: what stays exposed is the FIRST upload and the LAST download, so those two slices are one crop each
-  // and the rest of the batch is split evenly
-  int in_b[emd_engine::kSlices + 1], out_b[emd_engine::kSlices + 1];
-  int nin = 0, nout = 0;
-  {
-    const int k = std::min(K, n), rest = n - 1, parts = std::max(k - 1, 1);
-    in_b[nin++] = 0;
-    if (k > 1) in_b[nin++] = 1;
-    for (int i = 1; i <= parts && k > 1; ++i) { const int b = 1 + (int)((long long)rest * i / parts); if (b > in_b[nin - 1]) in_b[nin++] = b; }
-    if (k <= 1) in_b[nin++] = n;
-    out_b[nout++] = 0;
-    for (int i = 1; i <= parts && k > 1; ++i) { const int b = (int)((long long)rest * i / parts); if (b > out_b[nout - 1]) out_b[nout++] = b; }
-    out_b[nout++] = n;
-  }
-  const int n_in = nin - 1, n_out = nout - 1;   // number of slices each way (<= kSlices)
-  int head = 1;         // the steps of the first layer (its depthwise and pointwise halves)
-  while (head < last && e->steps[head].layer == e->steps[0].layer) ++head;
-  int in_free_at = head;   // the step after which the staging copy of the crops is dead (a fused depthwise reads at the next step)
-  for (int i = head; i < last; ++i)
-    if (e->steps[i].in.t == e->t_input) in_free_at = std::min(i + 1, last - 1);
+  int stem = 1;         // the steps of the first layer (its depthwise and pointwise halves)
+  while (stem < last && e->steps[stem].layer == e->steps[0].layer) ++stem;
+  // phases: [0, stem) sliced, [stem, head_end] per half, (head_end, tail_start) whole batch, [tail_start, last) per half, last sliced
+  const bool halves = !no_halves && e->head_end >= stem && e->tail_start <= last && n >= 16;
+  const int head_end = halves ? e->head_end : stem - 1, tail_start = halves ? e->tail_start : last;
+  const int nh = halves ? 2 : 1, h_split = halves ? n / 2 : n;
   e->last_n = n; e->last_et = c.et;
   auto step = [&](int i, int b0, int nb) -> int {
     c.b0 = b0; c.n = nb;
@@ -713,39 +719,86 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
     c.b0 = 0; c.n = n;
     return r == cudaSuccess ? EMD_OK : fail(e, EMD_ECUDA, "step %s: %s", e->steps[i].name.c_str(), cudaGetErrorString(r));
   };
-  int rc;
-  if (h_in) {
-    if (!first_pass) CU(e, cudaStreamWaitEvent(e->copy_in, e->ev_in_free, 0));      // the pass before has read the staging buffer
-    for (int q = 0; q < n_in; ++q) {
-      const int b0 = in_b[q], nb = in_b[q + 1] - b0;
-      CU(e, cudaMemcpyAsync(const_cast<float*>(d_in) + b0 * per, h_in + b0 * per, nb * per * 4, cudaMemcpyHostToDevice, e->copy_in));
-      CU(e, cudaEventRecord(e->ev_sl_in[q], e->copy_in));
+  // boundaries of up to k slices of [lo, hi) into b[]; single = 1: the first slice is one crop (the exposed upload),
+  // single = 2: the last one (the exposed download); returns the number of slices
+  auto slices = [](int lo, int hi, int k, int single, int* b) -> int {
+    const int m = hi - lo;
+    k = std::max(1, std::min(k, m));
+    int nb = 0;
+    b[nb++] = lo;
+    if (k > 1) {
+      const int body_lo = lo + (single == 1 ? 1 : 0), body_hi = hi - (single == 2 ? 1 : 0), parts = (single ? k - 1 : k);
+      if (single == 1) b[nb++] = body_lo;
+      for (int i = 1; i <= parts; ++i) {
+        const int v = body_lo + (int)((long long)(body_hi - body_lo) * i / parts);
+        if (v > b[nb - 1]) b[nb++] = v;
+      }
     }
-    for (int q = 0; q < n_in; ++q) {
-      const int b0 = in_b[q], nb = in_b[q + 1] - b0;
-      CU(e, cudaStreamWaitEvent(s, e->ev_sl_in[q], 0));
-      for (int i = 0; i < head; ++i)
-        if ((rc = step(i, b0, nb))) return rc;
+    if (b[nb - 1] != hi) b[nb++] = hi;
+    return nb - 1;
+  };
+  int last_input_reader = stem - 1;   // the staging copy of the crops is dead after this step (a fused depthwise reads at the next one)
+  for (int i = stem; i < last; ++i)
+    if (e->steps[i].in.t == e->t_input) last_input_reader = std::min(i + 1, last - 1);
+  int rc, ev = 0;
+  if (h_in && !first_pass) CU(e, cudaStreamWaitEvent(e->copy_in, e->ev_in_free, 0));   // the pass before has read the staging buffer
+  int bounds[emd_engine::kSlices + 2];
+  if (h_in) {           // all uploads are queued up front, in order; the compute stream waits slice by slice
+    for (int h = 0; h < nh; ++h) {
+      const int lo = h == 0 ? 0 : h_split, hi = (h == nh - 1) ? n : h_split;
+      const int ns = slices(lo, hi, K / nh, h == 0 ? 1 : 0, bounds);
+      for (int q = 0; q < ns; ++q, ++ev) {
+        const int b0 = bounds[q], nb = bounds[q + 1] - b0;
+        CU(e, cudaMemcpyAsync(const_cast<float*>(d_in) + b0 * per, h_in + b0 * per, nb * per * 4, cudaMemcpyHostToDevice, e->copy_in));
+        CU(e, cudaEventRecord(e->ev_sl_in[ev], e->copy_in));
+      }
     }
-  } else {
-    for (int i = 0; i < head; ++i)
-      if ((rc = step(i, 0, n))) return rc;
   }
-  for (int i = head; i < last; ++i) {
+  ev = 0;
+  for (int h = 0; h < nh; ++h) {
+    const int lo = h == 0 ? 0 : h_split, hi = (h == nh - 1) ? n : h_split;
+    if (h_in) {
+      const int ns = slices(lo, hi, K / nh, h == 0 ? 1 : 0, bounds);
+      for (int q = 0; q < ns; ++q, ++ev) {
+        const int b0 = bounds[q], nb = bounds[q + 1] - b0;
+        CU(e, cudaStreamWaitEvent(s, e->ev_sl_in[ev], 0));
+        for (int i = 0; i < stem; ++i)
+          if ((rc = step(i, b0, nb))) return rc;
+      }
+    } else {
+      for (int i = 0; i < stem; ++i)
+        if ((rc = step(i, lo, hi - lo))) return rc;
+    }
+    for (int i = stem; i <= head_end; ++i) {
+      if ((rc = step(i, lo, hi - lo))) return rc;
+      if (h_in && h == nh - 1 && i == last_input_reader) CU(e, cudaEventRecord(e->ev_in_free, s));
+    }
+  }
+  if (h_in && last_input_reader < stem) CU(e, cudaEventRecord(e->ev_in_free, s));
+  for (int i = head_end + 1; i < tail_start; ++i) {
     if ((rc = step(i, 0, n))) return rc;
-    if (h_in && i == in_free_at) CU(e, cudaEventRecord(e->ev_in_free, s));   // nothing later reads the crops
+    if (h_in && i == last_input_reader) CU(e, cudaEventRecord(e->ev_in_free, s));
   }
-  if (h_out) {
-    if (!first_pass) CU(e, cudaStreamWaitEvent(s, e->ev_out_free, 0));              // the D2H copies of the pass before have drained
-    for (int q = 0; q < n_out; ++q) {
-      const int b0 = out_b[q], nb = out_b[q + 1] - b0;
-      if ((rc = step(last, b0, nb))) return rc;
-      CU(e, cudaEventRecord(e->ev_sl_fin[q], s));
-      CU(e, cudaStreamWaitEvent(e->copy_out, e->ev_sl_fin[q], 0));
-      CU(e, cudaMemcpyAsync(h_out + b0 * per, d_out + b0 * per, nb * per * 4, cudaMemcpyDeviceToHost, e->copy_out));
+  if (h_out && !first_pass) CU(e, cudaStreamWaitEvent(s, e->ev_out_free, 0));         // the D2H copies of the pass before have drained
+  ev = 0;
+  for (int h = 0; h < nh; ++h) {
+    const int lo = h == 0 ? 0 : h_split, hi = (h == nh - 1) ? n : h_split;
+    for (int i = tail_start; i < last; ++i) {
+      if ((rc = step(i, lo, hi - lo))) return rc;
+      if (h_in && i == last_input_reader) CU(e, cudaEventRecord(e->ev_in_free, s));   // (only if the tail still read the crops)
     }
-    CU(e, cudaEventRecord(e->ev_out_free, e->copy_out));
-  } else if ((rc = step(last, 0, n))) return rc;
+    if (h_out) {
+      const int nsl = slices(lo, hi, K / nh, h == nh - 1 ? 2 : 0, bounds);   // the very last download is one crop
+      for (int q = 0; q < nsl; ++q, ++ev) {
+        const int b0 = bounds[q], nb = bounds[q + 1] - b0;
+        if ((rc = step(last, b0, nb))) return rc;
+        CU(e, cudaEventRecord(e->ev_sl_fin[ev], s));
+        CU(e, cudaStreamWaitEvent(e->copy_out, e->ev_sl_fin[ev], 0));
+        CU(e, cudaMemcpyAsync(h_out + b0 * per, d_out + b0 * per, nb * per * 4, cudaMemcpyDeviceToHost, e->copy_out));
+      }
+    } else if ((rc = step(last, lo, hi - lo))) return rc;
+  }
+  if (h_out) CU(e, cudaEventRecord(e->ev_out_free, e->copy_out));
   return EMD_OK;
 }
 

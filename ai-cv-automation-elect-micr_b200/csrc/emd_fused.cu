@@ -212,18 +212,22 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
     s_scale[i] = i < p.Cout ? p.scale[i] : 0.f;
     s_shift[i] = i < p.Cout ? p.shift[i] : 0.f;
   }
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kMaxStages; ++s) {
-      mbar_init(bar_afull + 8u * s, kDw ? kGroupWarps : 1);   // dw: one arrive per math warp of the group; taps: expect_tx arrive
-      mbar_init(bar_aempty + 8u * s, 1);
-      mbar_init(bar_bfull + 8u * s, 1);
-      mbar_init(bar_bempty + 8u * s, 1);
-      mbar_init(bar_hfull + 8u * s, 1);
-      mbar_init(bar_hempty + 8u * s, kGroupWarps);
-    }
+  // barrier set-up spread over the first threads (one pipeline stage each) instead of ~55 serial inits in thread 0: the
+  // prologue is part of the fixed cost every launch pays
+  if (threadIdx.x < kMaxStages) {
+    const uint32_t s = threadIdx.x;
+    mbar_init(bar_afull + 8u * s, kDw ? kGroupWarps : 1);   // dw: one arrive per math warp of the group; taps: expect_tx arrive
+    mbar_init(bar_aempty + 8u * s, 1);
+    mbar_init(bar_bfull + 8u * s, 1);
+    mbar_init(bar_bempty + 8u * s, 1);
+    mbar_init(bar_hfull + 8u * s, 1);
+    mbar_init(bar_hempty + 8u * s, kGroupWarps);
+    fence_barrier_init();
+  } else if (threadIdx.x == 32) {
     for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, (kPair ? 2 : 1) * kEpiWarps); }
     for (int i = 0; i < kMaxRing; ++i) mbar_init(bar_rfull + 8u * i, 1);
     fence_barrier_init();
+  } else if (threadIdx.x == 64) {
     prefetch_tmap(&tmap_in);
     for (int v = 0; v < a.nvar; ++v) prefetch_tmap(&tmaps_out.m[v]);
     if (kRes) prefetch_tmap(&tmap_res);
