@@ -711,7 +711,9 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
   // phases: [0, stem) sliced, [stem, head_end] per half, (head_end, tail_start) whole batch, [tail_start, last) per half, last sliced
   const bool halves = !no_halves && e->head_end >= stem && e->tail_start <= last && n >= 16;
   const int head_end = halves ? e->head_end : stem - 1, tail_start = halves ? e->tail_start : last;
-  const int nh = halves ? 2 : 1, h_split = halves ? n / 2 : n;
+  static const int parts_env = getenv("EMD_IO_PARTS") ? atoi(getenv("EMD_IO_PARTS")) : 0;   // tuning switch: 2 (default) or 4 parts
+  const int nh = halves ? (parts_env == 4 && n >= 32 ? 4 : 2) : 1;
+  auto part_lo = [&](int h) { return (int)((long long)n * h / nh); };
   e->last_n = n; e->last_et = c.et;
   auto step = [&](int i, int b0, int nb) -> int {
     c.b0 = b0; c.n = nb;
@@ -745,7 +747,7 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
   int bounds[emd_engine::kSlices + 2];
   if (h_in) {           // all uploads are queued up front, in order; the compute stream waits slice by slice
     for (int h = 0; h < nh; ++h) {
-      const int lo = h == 0 ? 0 : h_split, hi = (h == nh - 1) ? n : h_split;
+      const int lo = part_lo(h), hi = part_lo(h + 1);
       const int ns = slices(lo, hi, K / nh, h == 0 ? 1 : 0, bounds);
       for (int q = 0; q < ns; ++q, ++ev) {
         const int b0 = bounds[q], nb = bounds[q + 1] - b0;
@@ -756,7 +758,7 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
   }
   ev = 0;
   for (int h = 0; h < nh; ++h) {
-    const int lo = h == 0 ? 0 : h_split, hi = (h == nh - 1) ? n : h_split;
+    const int lo = part_lo(h), hi = part_lo(h + 1);
     if (h_in) {
       const int ns = slices(lo, hi, K / nh, h == 0 ? 1 : 0, bounds);
       for (int q = 0; q < ns; ++q, ++ev) {
@@ -782,7 +784,7 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
   if (h_out && !first_pass) CU(e, cudaStreamWaitEvent(s, e->ev_out_free, 0));         // the D2H copies of the pass before have drained
   ev = 0;
   for (int h = 0; h < nh; ++h) {
-    const int lo = h == 0 ? 0 : h_split, hi = (h == nh - 1) ? n : h_split;
+    const int lo = part_lo(h), hi = part_lo(h + 1);
     for (int i = tail_start; i < last; ++i) {
       if ((rc = step(i, lo, hi - lo))) return rc;
       if (h_in && i == last_input_reader) CU(e, cudaEventRecord(e->ev_in_free, s));   // (only if the tail still read the crops)
