@@ -148,6 +148,13 @@ def test_sliced_host_io_matches_device_io(emd, setup):
         out_host = torch.empty((n, S, S), dtype=torch.float32).pin_memory()
         eng.forward(dev, out=out_host, mode="bf16")                                               # device in, host out
         np.testing.assert_array_equal(out_host.numpy(), ref)
+    # variant B (different ASPP, no in-graph clip) through the same sliced / half-batch route
+    eb = emd.Engine(cropsize=S, max_batch=16, variant="B")
+    eb.load_weights(emd.weights.pack(emd.weights.init_reference_weights(0, "B"), "B"))
+    crops = rng.random((16, S, S)).astype(np.float32)
+    ref = eb.forward(torch.from_numpy(crops).cuda(), mode="bf16")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(eb.forward(crops, mode="bf16"), ref.cpu().numpy())
     # FP32 mode takes the same route (different first steps: no fused stem)
     crops = rng.random((20, S, S)).astype(np.float32)
     ref = eng.forward(torch.from_numpy(crops).cuda(), mode="fp32")
