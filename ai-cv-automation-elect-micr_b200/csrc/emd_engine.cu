@@ -98,6 +98,7 @@ struct emd_engine {
   bool use_graphs = true;
   int graph_max_n = 32;
   std::map<int, GraphSlot> graphs;
+  std::map<int, GraphSlot> mid_graphs;   // whole-batch middle section of the host-buffer pass (run_network_sliced)
   float *g_in = nullptr, *g_out = nullptr;
   long long graph_replays = 0;
 };
@@ -107,6 +108,8 @@ namespace {
 void drop_graphs(emd_engine* e) {
   for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   e->graphs.clear();
+  for (auto& kv : e->mid_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  e->mid_graphs.clear();
 }
 
 int fail(emd_engine* e, int code, const char* fmt, ...) {
@@ -777,7 +780,42 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
     }
   }
   if (h_in && last_input_reader < stem) CU(e, cudaEventRecord(e->ev_in_free, s));
-  for (int i = head_end + 1; i < tail_start; ++i) {
+  // the whole-batch middle section (the 32x32-resolution trunk: ~90 small kernels) is replayed from a CUDA graph from its
+  // second use on, like the device-resident pass; only when nothing but kernel launches happens inside it
+  bool replayed = false;
+  static const bool no_mid_graph = getenv("EMD_ENABLE_MID_GRAPH") == nullptr;   // opt-in until measured on the GPU box
+  bool mid_ok = halves && e->use_graphs && !no_mid_graph && last_input_reader <= head_end;
+  for (int i = head_end + 1; i < tail_start && mid_ok; ++i)          // no caller-owned buffer inside the captured range
+    for (int t : {e->steps[i].in.t, e->steps[i].out.t, e->steps[i].res.t})
+      if (t == e->t_input || t == e->t_output) mid_ok = false;
+  if (mid_ok) {
+    GraphSlot& g = e->mid_graphs[n * 4 + mode];
+    if (g.calls++ >= 1 && !g.failed) {
+      if (!g.exec) {
+        cudaGraph_t graph = nullptr;
+        cudaError_t r = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+        int crc = EMD_OK;
+        if (r == cudaSuccess) {
+          const long long l0 = e->launches, u0 = e->umma_launches;
+          for (int i = head_end + 1; i < tail_start && crc == EMD_OK; ++i) crc = step(i, 0, n);
+          g.launches = e->launches - l0; g.umma_launches = e->umma_launches - u0;
+          e->launches = l0; e->umma_launches = u0;
+          r = cudaStreamEndCapture(s, &graph);
+        }
+        if (r != cudaSuccess || crc != EMD_OK || !graph || cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
+          cudaGetLastError();
+          g.failed = true; g.exec = nullptr;
+        }
+        if (graph) cudaGraphDestroy(graph);
+      }
+      if (g.exec) {
+        CU(e, cudaGraphLaunch(g.exec, s));
+        e->launches += g.launches; e->umma_launches += g.umma_launches;
+        replayed = true;
+      }
+    }
+  }
+  for (int i = head_end + 1; i < tail_start && !replayed; ++i) {
     if ((rc = step(i, 0, n))) return rc;
     if (h_in && i == last_input_reader) CU(e, cudaEventRecord(e->ev_in_free, s));
   }
