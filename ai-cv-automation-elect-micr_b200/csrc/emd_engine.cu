@@ -783,7 +783,7 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
   // the whole-batch middle section (the 32x32-resolution trunk: ~90 small kernels) is replayed from a CUDA graph from its
   // second use on, like the device-resident pass; only when nothing but kernel launches happens inside it
   bool replayed = false;
-  static const bool no_mid_graph = getenv("EMD_ENABLE_MID_GRAPH") == nullptr;   // opt-in until measured on the GPU box
+  static const bool no_mid_graph = getenv("EMD_DISABLE_MID_GRAPH") != nullptr;   // A/B switch (+0.2..0.9 % end to end)
   bool mid_ok = halves && e->use_graphs && !no_mid_graph && last_input_reader <= head_end;
   for (int i = head_end + 1; i < tail_start && mid_ok; ++i)          // no caller-owned buffer inside the captured range
     for (int t : {e->steps[i].in.t, e->steps[i].out.t, e->steps[i].res.t})
