@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("EMD_LIB") or os.path.join(_HERE, "libemd.so")   # EMD
 
 EMD_MODE_FP32, EMD_MODE_BF16, EMD_MODE_FP16 = 0, 1, 2
 EMD_VARIANT_A, EMD_VARIANT_B = 0, 1
-EMD_FLAG_PREPROCESS, EMD_FLAG_POSTPROCESS, EMD_FLAG_INPUT_F64 = 1, 2, 4
+EMD_FLAG_PREPROCESS, EMD_FLAG_POSTPROCESS, EMD_FLAG_INPUT_F64, EMD_FLAG_OUTPUT_F32 = 1, 2, 4, 8
 
 MODES = {"fp32": EMD_MODE_FP32, "bf16": EMD_MODE_BF16, "fp16": EMD_MODE_FP16}
 
@@ -33,6 +33,7 @@ SIGNATURES = {
     "emd_gather_crops": (_I, [_P, _P, _I, _I, _IP, _IP, _I, _I, _I, _P, _P]),
     "emd_stitch": (_I, [_P, _P, _IP, _IP, _I, _I, _I, _I, _I, _I, _P, _P]),
     "emd_denoise_image": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "emd_denoise_stream": (_I, [_P, C.POINTER(_P), _I, _I, _I, _I, _I, _I, C.POINTER(_P), _P]),
     "emd_quality": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "emd_set_keep_activations": (_I, [_P, _I]),
     "emd_get_activation": (_I, [_P, C.c_char_p, _P, _SZ, _IP]),
@@ -40,6 +41,9 @@ SIGNATURES = {
     "emd_kernel_launches": (C.c_longlong, [_P]),
     "emd_tensor_core_launches": (C.c_longlong, [_P]),
     "emd_graph_replays": (C.c_longlong, [_P]),
+    "emd_counter": (C.c_longlong, [_P, C.c_char_p]),
+    "emd_set_option": (_I, [_P, C.c_char_p, C.c_longlong]),
+    "emd_get_option": (C.c_longlong, [C.c_char_p]),
     "emd_set_tensor_cores": (_I, [_P, _I]),
     "emd_set_profile": (_I, [_P, _I]),
     "emd_num_steps": (_I, [_P]),

@@ -60,7 +60,13 @@ struct BlobEntry { uint32_t rows, cols; size_t offset; };
 
 }  // namespace
 
-struct GraphSlot { cudaGraphExec_t exec = nullptr; int calls = 0; bool failed = false; long long launches = 0, umma_launches = 0; };
+// launch counters: all kernels, tcgen05 kernels, and conv launches by kernel kind (LaunchKind, emd_kernels.h)
+struct Counts {
+  long long launches = 0, umma = 0, kind[LK_COUNT] = {};
+  Counts& operator+=(const Counts& o) { launches += o.launches; umma += o.umma; for (int i = 0; i < LK_COUNT; ++i) kind[i] += o.kind[i]; return *this; }
+  Counts operator-(const Counts& o) const { Counts r = *this; r.launches -= o.launches; r.umma -= o.umma; for (int i = 0; i < LK_COUNT; ++i) r.kind[i] -= o.kind[i]; return r; }
+};
+struct GraphSlot { cudaGraphExec_t exec = nullptr; int calls = 0; bool failed = false; Counts cnt; };
 
 struct emd_engine {
   int device = 0, S = 512, variant = 0, max_batch = 1, num_sms = 148;
@@ -75,7 +81,7 @@ struct emd_engine {
   char* d_blob = nullptr; size_t blob_bytes = 0;
   std::map<std::string, BlobEntry> entries;
   std::vector<void*> w16_allocs;
-  long long launches = 0, umma_launches = 0;
+  Counts cnt;
   int last_n = 0, last_et = 0;
   // staging for host I/O of emd_forward
   float *d_stage_in = nullptr, *d_stage_out = nullptr;
@@ -93,10 +99,20 @@ struct emd_engine {
   double* d_sout = nullptr; size_t sout_bytes = 0;
   double* d_minmax = nullptr; void* d_partial = nullptr;
   int* d_origins = nullptr;  // ys then xs, 2*256 ints
+  // whole-micrograph path (emd_denoise_image / emd_denoise_stream): two slots, so that image i+1's upload + normalise + tile
+  // gather (pre stream) and image i-1's stitch + download (post stream) run under image i's network pass (compute stream)
+  struct ImgSlot {
+    char* d_raw = nullptr; size_t raw_bytes = 0;
+    float* d_norm = nullptr; size_t norm_bytes = 0;
+    float *d_crops = nullptr, *d_tiles = nullptr; size_t crops_bytes = 0, tiles_bytes = 0;
+    char* d_sout = nullptr; size_t sout_bytes = 0;
+    double* d_minmax = nullptr; char* d_partial = nullptr; size_t mm_bytes = 0, partial_bytes = 0;
+    cudaEvent_t ev_pre = nullptr, ev_net = nullptr, ev_post = nullptr;
+  } slots[2];
+  cudaStream_t s_pre = nullptr, s_post = nullptr;
+  cudaEvent_t ev_img_start = nullptr;
   std::vector<cudaEvent_t> events;
   // CUDA graphs of whole passes for small batches
-  bool use_graphs = true;
-  int graph_max_n = 32;
   std::map<int, GraphSlot> graphs;
   std::map<int, GraphSlot> mid_graphs;   // whole-batch middle section of the host-buffer pass (run_network_sliced)
   float *g_in = nullptr, *g_out = nullptr;
@@ -503,24 +519,26 @@ View make_view(const ExecCtx& c, Ref r) {
 
 cudaError_t run_conv(ExecCtx& c, ConvParams& p, const Step& s) {
   emd_engine* e = c.e;
-  e->launches++;
+  e->cnt.launches++;
+  auto tc = [&](int kind, cudaError_t r) { e->cnt.umma++; e->cnt.kind[kind]++; return r; };
   if (c.et != ET_F32 && e->use_umma && final_tma_supported(p, c.et)) {
     p.w = s.wr[c.et];
-    if (final_umma_supported(p, c.et)) {
-      e->umma_launches++;
-      return launch_final_umma(p, s.scale0, s.shift0, c.et, e->num_sms, c.s);
-    }
+    if (final_umma_supported(p, c.et)) return tc(LK_FINAL_UMMA, launch_final_umma(p, s.scale0, s.shift0, c.et, e->num_sms, c.s));
+    e->cnt.kind[LK_FINAL_TMA]++;
     return launch_final_tma(p, s.scale0, s.shift0, c.et, e->num_sms, c.s);
   }
   if (c.et != ET_F32 && e->use_umma && s.w16[c.et] && fused_supported(p, c.et, nullptr)) {
-    e->umma_launches++;
-    return launch_conv_fused(p, c.et, nullptr, e->num_sms, c.s);
+    const cudaError_t r = launch_conv_fused(p, c.et, nullptr, e->num_sms, c.s);
+    return tc(last_launch_kind(), r);
   }
-  if (c.et != ET_F32 && e->use_umma && s.w16[c.et] && umma_supported(p, c.et)) {
-    e->umma_launches++;
-    return launch_conv_umma(p, c.et, e->num_sms, c.s);
+  if (c.et != ET_F32 && e->use_umma && s.w16[c.et] && umma_supported(p, c.et))
+    return tc(LK_UMMA_GEN1, launch_conv_umma(p, c.et, e->num_sms, c.s));
+  if (c.et != ET_F32 && e->use_umma && tuning().strict) {   // a silent CUDA-core fallback would pass every test and cost 10x
+    e->err = "strict: no tensor-core kernel supports step " + s.name;
+    return cudaErrorNotSupported;
   }
   if (c.et != ET_F32 && s.wr[c.et]) p.w = s.wr[c.et];
+  e->cnt.kind[LK_SIMT]++;
   return launch_conv_simt(p, c.et, c.s);
 }
 
@@ -566,13 +584,19 @@ bool dw_fusable(const ExecCtx& c, int conv_idx, ConvParams* out) {
   return true;
 }
 
+int step_error(emd_engine* e, int idx, cudaError_t r) {
+  if (r == cudaErrorNotSupported && tuning().strict)
+    return fail(e, EMD_ESTATE, "step %s: no tensor-core kernel supports this shape and EMD_STRICT forbids the CUDA-core fallback", e->steps[idx].name.c_str());
+  return fail(e, EMD_ECUDA, "step %s: %s", e->steps[idx].name.c_str(), cudaGetErrorString(r));
+}
+
 cudaError_t run_step_impl(ExecCtx& c, int idx);
 cudaError_t run_step(ExecCtx& c, int idx) {
   Step& s = c.e->steps[idx];
-  const long long before = c.e->launches;
+  const long long before = c.e->cnt.launches;
   s.fused = false;
   cudaError_t r = run_step_impl(c, idx);
-  s.nlaunch = (int)(c.e->launches - before);
+  s.nlaunch = (int)(c.e->cnt.launches - before);
   return r;
 }
 
@@ -590,20 +614,20 @@ cudaError_t run_step_impl(ExecCtx& c, int idx) {
       p.N = c.n; p.OH = to.H; p.OW = to.W; p.stride = s.stride; p.rate = s.rate;
       p.pad = (s.stride == 1) ? s.rate : 0;  // TF SAME: symmetric `rate` at stride 1; 0 before / 1 after at stride 2 on even sizes
       p.w = s.dw; p.in_f32 = ti.external;
-      e->launches++;
+      e->cnt.launches++;
       if (e->use_umma && dw_tma_supported(p, c.et)) return launch_dw_tma(p, c.et, e->num_sms, c.s);
       if (e->use_umma && dw_s2_tma_supported(p, c.et)) return launch_dw_s2_tma(p, c.et, e->num_sms, c.s);
       return launch_dw3x3(p, c.et, c.s);
     }
     case SK_POOL: {
       PoolParams p{}; p.in = make_view(c, s.in); p.out = make_view(c, s.out); p.N = c.n;
-      e->launches++;
+      e->cnt.launches++;
       return launch_avgpool(p, c.et, c.s);
     }
     case SK_RESIZE: {
       ResizeParams p{}; p.in = make_view(c, s.in); p.out = make_view(c, s.out); p.N = c.n;
       p.scale = s.scale; p.shift = s.shift; p.relu6 = s.relu6;
-      e->launches++;
+      e->cnt.launches++;
       return launch_resize(p, c.et, c.s);
     }
     case SK_CONV: {
@@ -619,7 +643,7 @@ cudaError_t run_step_impl(ExecCtx& c, int idx) {
           p.dw = dws ? dws->dw : nullptr;
           p.w = (c.et != ET_F32 && s.wr[c.et]) ? s.wr[c.et] : s.w;
           p.scale = s.scale; p.shift = s.shift; p.istride = s.stride; p.relu6 = s.relu6;
-          e->launches++;
+          e->cnt.launches++;
           s.fused = dws != nullptr;
           return launch_stem(p, c.et, c.s);
         }
@@ -627,8 +651,9 @@ cudaError_t run_step_impl(ExecCtx& c, int idx) {
       ConvParams p{};
       if (dw_fusable(c, idx, &p)) {
         s.fused = true;
-        e->launches++;
-        e->umma_launches++;
+        e->cnt.launches++;
+        e->cnt.umma++;
+        e->cnt.kind[LK_FUSED_DW]++;
         return launch_conv_fused(p, c.et, e->steps[idx - 1].dw, e->num_sms, c.s);
       }
       p = ConvParams{};
@@ -660,9 +685,11 @@ cudaError_t run_step_impl(ExecCtx& c, int idx) {
           }
         }
       if (c.et != ET_F32 && e->use_umma && s.w16[c.et] && fused_multi_supported(ph, 4, c.et)) {
-        e->launches++;
-        e->umma_launches++;
-        return launch_conv_fused_multi(ph, 4, c.et, e->num_sms, c.s);   // one launch: work items = (input tile, phase)
+        e->cnt.launches++;
+        e->cnt.umma++;
+        const cudaError_t r = launch_conv_fused_multi(ph, 4, c.et, e->num_sms, c.s);   // one launch: work items = (input tile, phase)
+        e->cnt.kind[last_launch_kind()]++;
+        return r;
       }
       for (int v = 0; v < 4; ++v) {
         cudaError_t r = run_conv(c, ph[v], s);
@@ -684,7 +711,7 @@ int run_network_direct(emd_engine* e, const float* d_in, float* d_out, int n, in
   for (size_t i = 0; i < e->steps.size(); ++i) {
     if (e->profile) CU(e, cudaEventRecord(e->events[i], s));
     cudaError_t r = run_step(c, (int)i);
-    if (r != cudaSuccess) return fail(e, EMD_ECUDA, "step %s: %s", e->steps[i].name.c_str(), cudaGetErrorString(r));
+    if (r != cudaSuccess) return step_error(e, (int)i, r);
   }
   if (e->profile) {
     CU(e, cudaEventRecord(e->events[e->steps.size()], s));
@@ -705,8 +732,9 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
                        cudaStream_t s, bool first_pass) {
   ExecCtx c{e, mode == EMD_MODE_FP32 ? ET_F32 : (mode == EMD_MODE_BF16 ? ET_BF16 : ET_F16), n, s, d_in, d_out, {}};
   const size_t per = (size_t)e->S * e->S;
-  static const int k_env = getenv("EMD_IO_SLICES") ? atoi(getenv("EMD_IO_SLICES")) : 0;   // tuning switches
-  static const bool no_halves = getenv("EMD_DISABLE_HALVES") != nullptr;
+  const Tuning& tn = tuning();
+  const int k_env = tn.io_slices;
+  const bool no_halves = !tn.halves;
   const int K = k_env > 0 && k_env <= emd_engine::kSlices ? k_env : emd_engine::kSlices;
   const int last = (int)e->steps.size() - 1;
   int stem = 1;         // the steps of the first layer (its depthwise and pointwise halves)
@@ -714,7 +742,7 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
   // phases: [0, stem) sliced, [stem, head_end] per half, (head_end, tail_start) whole batch, [tail_start, last) per half, last sliced
   const bool halves = !no_halves && e->head_end >= stem && e->tail_start <= last && n >= 16;
   const int head_end = halves ? e->head_end : stem - 1, tail_start = halves ? e->tail_start : last;
-  static const int parts_env = getenv("EMD_IO_PARTS") ? atoi(getenv("EMD_IO_PARTS")) : 0;   // tuning switch: 2 (default) or 4 parts
+  const int parts_env = tn.io_parts;   // 2 (default) or 4 parts
   const int nh = halves ? (parts_env == 4 && n >= 32 ? 4 : 2) : 1;
   auto part_lo = [&](int h) { return (int)((long long)n * h / nh); };
   e->last_n = n; e->last_et = c.et;
@@ -722,7 +750,7 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
     c.b0 = b0; c.n = nb;
     cudaError_t r = run_step(c, i);
     c.b0 = 0; c.n = n;
-    return r == cudaSuccess ? EMD_OK : fail(e, EMD_ECUDA, "step %s: %s", e->steps[i].name.c_str(), cudaGetErrorString(r));
+    return r == cudaSuccess ? EMD_OK : step_error(e, i, r);
   };
   // boundaries of up to k slices of [lo, hi) into b[]; single = 1: the first slice is one crop (the exposed upload),
   // single = 2: the last one (the exposed download); returns the number of slices
@@ -783,8 +811,7 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
   // the whole-batch middle section (the 32x32-resolution trunk: ~90 small kernels) is replayed from a CUDA graph from its
   // second use on, like the device-resident pass; only when nothing but kernel launches happens inside it
   bool replayed = false;
-  static const bool no_mid_graph = getenv("EMD_DISABLE_MID_GRAPH") != nullptr;   // A/B switch (+0.2..0.9 % end to end)
-  bool mid_ok = halves && e->use_graphs && !no_mid_graph && last_input_reader <= head_end;
+  bool mid_ok = halves && tn.graphs && tn.mid_graph && last_input_reader <= head_end;   // mid_graph: +0.2..0.9 % end to end
   for (int i = head_end + 1; i < tail_start && mid_ok; ++i)          // no caller-owned buffer inside the captured range
     for (int t : {e->steps[i].in.t, e->steps[i].out.t, e->steps[i].res.t})
       if (t == e->t_input || t == e->t_output) mid_ok = false;
@@ -796,10 +823,10 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
         cudaError_t r = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
         int crc = EMD_OK;
         if (r == cudaSuccess) {
-          const long long l0 = e->launches, u0 = e->umma_launches;
+          const Counts c0 = e->cnt;
           for (int i = head_end + 1; i < tail_start && crc == EMD_OK; ++i) crc = step(i, 0, n);
-          g.launches = e->launches - l0; g.umma_launches = e->umma_launches - u0;
-          e->launches = l0; e->umma_launches = u0;
+          g.cnt = e->cnt - c0;
+          e->cnt = c0;
           r = cudaStreamEndCapture(s, &graph);
         }
         if (r != cudaSuccess || crc != EMD_OK || !graph || cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
@@ -810,7 +837,7 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
       }
       if (g.exec) {
         CU(e, cudaGraphLaunch(g.exec, s));
-        e->launches += g.launches; e->umma_launches += g.umma_launches;
+        e->cnt += g.cnt;
         replayed = true;
       }
     }
@@ -847,14 +874,14 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
 // pass (the first runs directly so every kernel's attributes are set outside capture); the network reads / writes fixed
 // staging buffers inside the graph, with a device-to-device copy of the crops either side.
 int run_network(emd_engine* e, const float* d_in, float* d_out, int n, int mode, cudaStream_t s) {
-  if (!e->use_graphs || e->profile || e->keep || n > e->graph_max_n) return run_network_direct(e, d_in, d_out, n, mode, s);
+  if (!tuning().graphs || e->profile || e->keep || n > tuning().graph_max_n) return run_network_direct(e, d_in, d_out, n, mode, s);
   const int key = n * 4 + mode;
   GraphSlot& g = e->graphs[key];
   const size_t bytes = (size_t)n * e->S * e->S * sizeof(float);
   if (g.calls++ == 0 || g.failed) return run_network_direct(e, d_in, d_out, n, mode, s);
   if (!g.exec) {
     if (!e->g_in) {
-      const size_t cap = (size_t)e->graph_max_n * e->S * e->S * sizeof(float);
+      const size_t cap = (size_t)e->max_batch * e->S * e->S * sizeof(float);
       CU(e, cudaMalloc(&e->g_in, cap));
       CU(e, cudaMalloc(&e->g_out, cap));
     }
@@ -862,10 +889,10 @@ int run_network(emd_engine* e, const float* d_in, float* d_out, int n, int mode,
     cudaError_t r = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
     int rc = EMD_OK;
     if (r == cudaSuccess) {
-      const long long l0 = e->launches, u0 = e->umma_launches;
+      const Counts c0 = e->cnt;
       rc = run_network_direct(e, e->g_in, e->g_out, n, mode, s);
-      g.launches = e->launches - l0; g.umma_launches = e->umma_launches - u0;
-      e->launches = l0; e->umma_launches = u0;     // nothing ran yet: the replay below counts them
+      g.cnt = e->cnt - c0;
+      e->cnt = c0;                                  // nothing ran yet: the replay below counts them
       r = cudaStreamEndCapture(s, &graph);
     }
     if (r != cudaSuccess || rc != EMD_OK || !graph || cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
@@ -880,8 +907,7 @@ int run_network(emd_engine* e, const float* d_in, float* d_out, int n, int mode,
   CU(e, cudaGraphLaunch(g.exec, s));
   CU(e, cudaMemcpyAsync(d_out, e->g_out, bytes, cudaMemcpyDeviceToDevice, s));
   e->last_n = n; e->last_et = mode == EMD_MODE_FP32 ? ET_F32 : (mode == EMD_MODE_BF16 ? ET_BF16 : ET_F16);
-  e->launches += g.launches;
-  e->umma_launches += g.umma_launches;
+  e->cnt += g.cnt;
   e->graph_replays++;
   return EMD_OK;
 }
@@ -928,18 +954,7 @@ int emd_create(emd_engine** out, int device, int cropsize, int variant, int max_
   if (device < 0 || device >= ndev) return fail(nullptr, EMD_EINVAL, "device %d of %d", device, ndev);
   emd_engine* e = new emd_engine();
   e->device = device; e->S = cropsize; e->variant = variant; e->max_batch = max_batch;
-  const char* env = getenv("EMD_DISABLE_UMMA");
-  e->use_umma = !(env && env[0] == '1');
-  env = getenv("EMD_DISABLE_GRAPH");
-  e->use_graphs = !(env && env[0] == '1');
-  env = getenv("EMD_GRAPH_MAX_N");   // tuning switch: largest batch replayed from a CUDA graph
-  if (env && atoi(env) > 0) e->graph_max_n = atoi(env);
-  env = getenv("EMD_DISABLE_TMA");
-  umma_set_tma(!(env && env[0] == '1'));
-  env = getenv("EMD_DISABLE_PAIR");
-  fused_set_pair(!(env && env[0] == '1'));
-  env = getenv("EMD_DISABLE_FUSED");
-  fused_set_enabled(!(env && env[0] == '1'));
+  e->use_umma = tuning().umma != 0;
 #define CUC(call)                                                                                       \
   do {                                                                                                  \
     cudaError_t _r = (call);                                                                            \
@@ -983,7 +998,13 @@ int emd_destroy(emd_engine* e) {
                   (void*)e->d_img, (void*)e->d_crops, (void*)e->d_tiles, (void*)e->d_sout, (void*)e->d_minmax,
                   e->d_partial, (void*)e->d_origins})
     if (p) cudaFree(p);
-  for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  for (auto& sl : e->slots) {
+    for (void* p : {(void*)sl.d_raw, (void*)sl.d_norm, (void*)sl.d_crops, (void*)sl.d_tiles, (void*)sl.d_sout, (void*)sl.d_minmax, (void*)sl.d_partial})
+      if (p) cudaFree(p);
+    for (cudaEvent_t ev : {sl.ev_pre, sl.ev_net, sl.ev_post}) if (ev) cudaEventDestroy(ev);
+  }
+  if (e->s_pre) { cudaStreamDestroy(e->s_pre); cudaStreamDestroy(e->s_post); cudaEventDestroy(e->ev_img_start); }
+  drop_graphs(e);
   if (e->g_in) { cudaFree(e->g_in); cudaFree(e->g_out); }
   for (auto ev : e->events) cudaEventDestroy(ev);
   if (e->copy_in) {
@@ -1006,15 +1027,26 @@ int emd_load_weights(emd_engine* e, const void* blob, size_t nbytes) {
   BlobHeader h; memcpy(&h, b, sizeof h);
   if (memcmp(h.magic, "EMDW0001", 8) != 0) return fail(e, EMD_EINVAL, "bad blob magic");
   if ((int)h.variant != e->variant) return fail(e, EMD_EINVAL, "blob is variant %u, engine is %d", h.variant, e->variant);
-  if (nbytes < sizeof h + (size_t)h.n_entries * sizeof(BlobRecord)) return fail(e, EMD_EINVAL, "blob truncated");
-  drop_graphs(e);
-  e->entries.clear();
+  if ((nbytes - sizeof h) / sizeof(BlobRecord) < h.n_entries) return fail(e, EMD_EINVAL, "blob truncated");
+  // parse into a fresh table first: a malformed blob leaves the engine exactly as it was
+  std::map<std::string, BlobEntry> entries;
   for (uint32_t i = 0; i < h.n_entries; ++i) {
-    BlobRecord r; memcpy(&r, b + sizeof h + i * sizeof r, sizeof r);
+    BlobRecord r; memcpy(&r, b + sizeof h + (size_t)i * sizeof r, sizeof r);
     r.name[47] = 0;
-    if (r.offset + (size_t)r.rows * r.cols * 4 > nbytes) return fail(e, EMD_EINVAL, "blob entry %s out of range", r.name);
-    e->entries[r.name] = BlobEntry{r.rows, r.cols, (size_t)r.offset};
+    const uint64_t elems = (uint64_t)r.rows * r.cols;                    // < 2^64: both factors are 32-bit
+    if ((r.offset & 3) || r.offset > nbytes || elems > (nbytes - r.offset) / 4)
+      return fail(e, EMD_EINVAL, "blob entry %s out of range or misaligned", r.name);
+    entries[r.name] = BlobEntry{r.rows, r.cols, (size_t)r.offset};
   }
+  // from here on the old weights are gone: the engine is unusable until the new ones are bound
+  CU(e, cudaStreamSynchronize(e->stream));
+  e->weights_loaded = false;
+  drop_graphs(e);
+  for (Step& s : e->steps) {
+    s.w = s.scale = s.shift = s.dw = nullptr;
+    for (int t = 0; t < 3; ++t) { s.w16[t] = nullptr; s.wr[t] = nullptr; }
+  }
+  e->entries.swap(entries);
   if (e->d_blob) { cudaFree(e->d_blob); e->d_blob = nullptr; }
   for (void* p : e->w16_allocs) cudaFree(p);
   e->w16_allocs.clear();
@@ -1067,8 +1099,7 @@ int emd_forward(emd_engine* e, const float* crops, int n, float* out, int mode, 
   CU(e, cudaEventRecord(e->ev_start, s));          // work already queued on the caller's stream comes first
   CU(e, cudaStreamWaitEvent(e->copy_in, e->ev_start, 0));
   CU(e, cudaStreamWaitEvent(e->copy_out, e->ev_start, 0));
-  static const bool no_slices = getenv("EMD_DISABLE_SLICED_IO") != nullptr;   // A/B switch: the two-chunk pipeline below
-  const bool sliceable = !no_slices && !e->profile && !e->keep && e->steps.size() >= 3 && e->steps.front().in.t == e->t_input &&
+  const bool sliceable = tuning().sliced_io &&   // A/B switch: the two-chunk pipeline below !e->profile && !e->keep && e->steps.size() >= 3 && e->steps.front().in.t == e->t_input &&
                          e->steps.back().out.t == e->t_output && e->steps.back().in.t != e->t_input;
   if (sliceable && n >= 16 && e->max_batch >= 16) {
     // passes of up to max_batch crops (balanced, so that no pass is a small remainder)
@@ -1151,7 +1182,7 @@ int emd_normalise(emd_engine* e, const void* img, int in_f64, int H, int W, floa
   }
   CU(e, launch_minmax(d_src, in_f64, n, e->d_minmax, e->d_partial, s));
   CU(e, launch_normalise_apply(d_src, in_f64, n, e->d_minmax, d_dst, s));
-  e->launches += 3;
+  e->cnt.launches += 3;
   if (!out_dev) {
     CU(e, cudaMemcpyAsync(out, d_dst, n * 4, cudaMemcpyDeviceToHost, s));
     CU(e, cudaStreamSynchronize(s));
@@ -1187,7 +1218,7 @@ int emd_gather_crops(emd_engine* e, const float* img, int H, int W, const int* y
     d_dst = e->d_crops;
   }
   CU(e, launch_gather(d_src, H, W, e->d_origins, e->d_origins + 256, ny, nx, crop, d_dst, s));
-  e->launches++;
+  e->cnt.launches++;
   if (!out_dev) {
     CU(e, cudaMemcpyAsync(crops, d_dst, ncr, cudaMemcpyDeviceToHost, s));
     CU(e, cudaStreamSynchronize(s));
@@ -1215,8 +1246,8 @@ int emd_stitch(emd_engine* e, const float* tiles, const int* ys, const int* xs, 
     if ((rc = grow(e, &e->d_sout, &e->sout_bytes, nout))) return rc;
     d_dst = e->d_sout;
   }
-  CU(e, launch_stitch(d_src, e->d_origins, e->d_origins + 256, ny, nx, crop, H, W, clip, d_dst, s));
-  e->launches++;
+  CU(e, launch_stitch(d_src, e->d_origins, e->d_origins + 256, ny, nx, crop, H, W, clip, d_dst, 0, s));
+  e->cnt.launches++;
   if (!out_dev) {
     CU(e, cudaMemcpyAsync(out, d_dst, nout, cudaMemcpyDeviceToHost, s));
     CU(e, cudaStreamSynchronize(s));
@@ -1248,68 +1279,119 @@ int emd_quality(emd_engine* e, const float* a, const float* b, int n, int H, int
   double* d_partial = reinterpret_cast<double*>(e->d_q_partial);
   double* d_out = d_partial + quality_partial_bytes(n, H, W) / sizeof(double);
   CU(e, launch_quality(da, db, n, H, W, d_partial, d_out, s));
-  e->launches += 2;
+  e->cnt.launches += 2;
   CU(e, cudaMemcpyAsync(out, d_out, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CU(e, cudaStreamSynchronize(s));
   return EMD_OK;
 }
 
-int emd_denoise_image(emd_engine* e, const void* img, int H, int W, int overlap, int flags, int mode, double* out,
+// Core of the whole-micrograph path.  Three streams: `pre` (upload, min/max, normalise, tile gather), the caller's / engine's
+// compute stream `s` (network), `post` (stitch, download); image i uses slot i & 1.  One image = the same chain without overlap.
+static int denoise_images(emd_engine* e, const void* const* imgs, int count, int H, int W, int overlap, int flags, int mode,
+                          void* const* outs, cudaStream_t s) {
+  const int crop = e->S;
+  if (H < crop || W < crop) return fail(e, EMD_EINVAL, "image %dx%d smaller than the %d crop", H, W, crop);
+  if (overlap < 0 || overlap >= crop) return fail(e, EMD_EINVAL, "overlap %d outside [0,%d)", overlap, crop);
+  const bool f64 = flags & EMD_FLAG_INPUT_F64, out_f32 = flags & EMD_FLAG_OUTPUT_F32;
+  if (f64 && !(flags & EMD_FLAG_PREPROCESS)) return fail(e, EMD_EINVAL, "float64 input needs EMD_FLAG_PREPROCESS");
+  for (int i = 0; i < count; ++i)
+    if (!imgs[i] || !outs[i]) return fail(e, EMD_EINVAL, "image %d: NULL pointer", i);
+  int ys[256], xs[256], ny = 0, nx = 0;
+  if (H / (crop - overlap) + 1 > 256 || W / (crop - overlap) + 1 > 256) return fail(e, EMD_EINVAL, "image too large");
+  if (emd_plan_tiles(H, W, crop, overlap, ys, xs, &ny, &nx)) return fail(e, EMD_EINVAL, "bad tiling arguments");
+  int rc;
+  if ((rc = upload_origins(e, ys, xs, ny, nx, s))) return rc;
+  if (!e->s_pre) {
+    CU(e, cudaStreamCreateWithFlags(&e->s_pre, cudaStreamNonBlocking));
+    CU(e, cudaStreamCreateWithFlags(&e->s_post, cudaStreamNonBlocking));
+    CU(e, cudaEventCreateWithFlags(&e->ev_img_start, cudaEventDisableTiming));
+    for (auto& sl : e->slots) {
+      CU(e, cudaEventCreateWithFlags(&sl.ev_pre, cudaEventDisableTiming));
+      CU(e, cudaEventCreateWithFlags(&sl.ev_net, cudaEventDisableTiming));
+      CU(e, cudaEventCreateWithFlags(&sl.ev_post, cudaEventDisableTiming));
+    }
+  }
+  const size_t npx = (size_t)H * W, esz = f64 ? 8 : 4, osz = out_f32 ? 4 : 8;
+  const int T = ny * nx;
+  const size_t per = (size_t)crop * crop, ncr = (size_t)T * per * 4;
+  const int nslots = count > 1 ? 2 : 1;
+  for (int k = 0; k < nslots; ++k) {          // all allocation up front: cudaMalloc / cudaFree would serialise the streams
+    auto& sl = e->slots[k];
+    if ((rc = grow(e, &sl.d_raw, &sl.raw_bytes, npx * esz))) return rc;
+    if ((rc = grow(e, &sl.d_norm, &sl.norm_bytes, npx * 4))) return rc;
+    if ((rc = grow(e, &sl.d_crops, &sl.crops_bytes, ncr))) return rc;
+    if ((rc = grow(e, &sl.d_tiles, &sl.tiles_bytes, ncr))) return rc;
+    if ((rc = grow(e, &sl.d_sout, &sl.sout_bytes, npx * 8))) return rc;
+    if ((rc = grow(e, reinterpret_cast<char**>(&sl.d_minmax), &sl.mm_bytes, 2 * sizeof(double)))) return rc;
+    if ((rc = grow(e, &sl.d_partial, &sl.partial_bytes, minmax_partial_bytes()))) return rc;
+  }
+  CU(e, cudaEventRecord(e->ev_img_start, s));            // the tile origins, and whatever the caller queued before, come first
+  CU(e, cudaStreamWaitEvent(e->s_pre, e->ev_img_start, 0));
+  CU(e, cudaStreamWaitEvent(e->s_post, e->ev_img_start, 0));
+  const int nchunks = (T + e->max_batch - 1) / e->max_batch, chunk = (T + nchunks - 1) / nchunks;   // balanced passes
+  bool any_host_out = false;
+  for (int i = 0; i < count; ++i) {
+    auto& sl = e->slots[i & 1];
+    // ---- pre: upload, normalise, gather ----
+    if (i >= 2) CU(e, cudaStreamWaitEvent(e->s_pre, sl.ev_net, 0));      // image i-2's network pass has read this slot's crops
+    const void* d_raw = imgs[i];
+    if (!is_device_ptr(imgs[i])) {
+      CU(e, cudaMemcpyAsync(sl.d_raw, imgs[i], npx * esz, cudaMemcpyHostToDevice, e->s_pre));
+      d_raw = sl.d_raw;
+    }
+    const float* d_norm = reinterpret_cast<const float*>(d_raw);
+    if (flags & EMD_FLAG_PREPROCESS) {
+      CU(e, launch_minmax(d_raw, f64, npx, sl.d_minmax, sl.d_partial, e->s_pre));
+      CU(e, launch_normalise_apply(d_raw, f64, npx, sl.d_minmax, sl.d_norm, e->s_pre));
+      e->cnt.launches += 3;
+      d_norm = sl.d_norm;
+    }
+    CU(e, launch_gather(d_norm, H, W, e->d_origins, e->d_origins + 256, ny, nx, crop, sl.d_crops, e->s_pre));
+    e->cnt.launches++;
+    CU(e, cudaEventRecord(sl.ev_pre, e->s_pre));
+    // ---- network ----
+    CU(e, cudaStreamWaitEvent(s, sl.ev_pre, 0));
+    if (i >= 2) CU(e, cudaStreamWaitEvent(s, sl.ev_post, 0));            // image i-2's stitch has read this slot's tiles
+    for (int c0 = 0; c0 < T; c0 += chunk) {
+      const int nb = std::min(chunk, T - c0);
+      if ((rc = run_network(e, sl.d_crops + c0 * per, sl.d_tiles + c0 * per, nb, mode, s))) return rc;
+    }
+    CU(e, cudaEventRecord(sl.ev_net, s));
+    // ---- post: stitch, download ----
+    CU(e, cudaStreamWaitEvent(e->s_post, sl.ev_net, 0));
+    const bool out_dev = is_device_ptr(outs[i]);
+    void* d_dst = out_dev ? outs[i] : sl.d_sout;
+    CU(e, launch_stitch(sl.d_tiles, e->d_origins, e->d_origins + 256, ny, nx, crop, H, W, (flags & EMD_FLAG_POSTPROCESS) ? 1 : 0,
+                        d_dst, out_f32 ? 1 : 0, e->s_post));
+    e->cnt.launches++;
+    if (!out_dev) {
+      CU(e, cudaMemcpyAsync(outs[i], d_dst, npx * osz, cudaMemcpyDeviceToHost, e->s_post));
+      any_host_out = true;
+    }
+    CU(e, cudaEventRecord(sl.ev_post, e->s_post));
+  }
+  for (int k = 0; k < nslots && k < count; ++k) CU(e, cudaStreamWaitEvent(s, e->slots[k].ev_post, 0));   // the caller's stream sees the results
+  if (any_host_out) CU(e, cudaStreamSynchronize(e->s_post));
+  return EMD_OK;
+}
+
+int emd_denoise_image(emd_engine* e, const void* img, int H, int W, int overlap, int flags, int mode, void* out,
                       void* stream) {
   if (!e || !img || !out) return EMD_EINVAL;
   int rc = check_mode(e, mode);
   if (rc) return rc;
-  const int crop = e->S;
-  if (H < crop || W < crop) return fail(e, EMD_EINVAL, "image %dx%d smaller than the %d crop", H, W, crop);
-  const bool f64 = flags & EMD_FLAG_INPUT_F64;
-  if (f64 && !(flags & EMD_FLAG_PREPROCESS)) return fail(e, EMD_EINVAL, "float64 input needs EMD_FLAG_PREPROCESS");
   CU(e, cudaSetDevice(e->device));
-  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
-  int ys[256], xs[256], ny = 0, nx = 0;
-  if (H / (crop - overlap) + 1 > 256 || W / (crop - overlap) + 1 > 256) return fail(e, EMD_EINVAL, "image too large");
-  if (emd_plan_tiles(H, W, crop, overlap, ys, xs, &ny, &nx)) return fail(e, EMD_EINVAL, "bad tiling arguments");
-  if ((rc = upload_origins(e, ys, xs, ny, nx, s))) return rc;
-  const size_t npx = (size_t)H * W, esz = f64 ? 8 : 4;
-  const int T = ny * nx;
-  const size_t ncr = (size_t)T * crop * crop * 4;
-  // image to device
-  const void* d_raw = img;
-  if (!is_device_ptr(img)) {
-    if ((rc = grow(e, reinterpret_cast<char**>(&e->d_img_raw), &e->img_raw_bytes, npx * esz))) return rc;
-    CU(e, cudaMemcpyAsync(e->d_img_raw, img, npx * esz, cudaMemcpyHostToDevice, s));
-    d_raw = e->d_img_raw;
-  }
-  const float* d_norm = reinterpret_cast<const float*>(d_raw);
-  if (flags & EMD_FLAG_PREPROCESS) {
-    if ((rc = grow(e, &e->d_img, &e->img_bytes, npx * 4))) return rc;
-    CU(e, launch_minmax(d_raw, f64, npx, e->d_minmax, e->d_partial, s));
-    CU(e, launch_normalise_apply(d_raw, f64, npx, e->d_minmax, e->d_img, s));
-    e->launches += 3;
-    d_norm = e->d_img;
-  }
-  if ((rc = grow(e, &e->d_crops, &e->crops_bytes, ncr))) return rc;
-  if ((rc = grow(e, &e->d_tiles, &e->tiles_bytes, ncr))) return rc;
-  CU(e, launch_gather(d_norm, H, W, e->d_origins, e->d_origins + 256, ny, nx, crop, e->d_crops, s));
-  e->launches++;
-  const size_t per = (size_t)crop * crop;
-  for (int c0 = 0; c0 < T; c0 += e->max_batch) {
-    const int nb = std::min(e->max_batch, T - c0);
-    if ((rc = run_network(e, e->d_crops + c0 * per, e->d_tiles + c0 * per, nb, mode, s))) return rc;
-  }
-  double* d_dst = out;
-  const bool out_dev = is_device_ptr(out);
-  if (!out_dev) {
-    if ((rc = grow(e, &e->d_sout, &e->sout_bytes, npx * 8))) return rc;
-    d_dst = e->d_sout;
-  }
-  CU(e, launch_stitch(e->d_tiles, e->d_origins, e->d_origins + 256, ny, nx, crop, H, W,
-                      (flags & EMD_FLAG_POSTPROCESS) ? 1 : 0, d_dst, s));
-  e->launches++;
-  if (!out_dev) {
-    CU(e, cudaMemcpyAsync(out, d_dst, npx * 8, cudaMemcpyDeviceToHost, s));
-    CU(e, cudaStreamSynchronize(s));
-  }
-  return EMD_OK;
+  return denoise_images(e, &img, 1, H, W, overlap, flags, mode, &out, stream ? (cudaStream_t)stream : e->stream);
+}
+
+int emd_denoise_stream(emd_engine* e, const void* const* imgs, int count, int H, int W, int overlap, int flags, int mode,
+                       void* const* outs, void* stream) {
+  if (!e || !imgs || !outs || count < 0) return EMD_EINVAL;
+  int rc = check_mode(e, mode);
+  if (rc) return rc;
+  if (count == 0) return EMD_OK;
+  CU(e, cudaSetDevice(e->device));
+  return denoise_images(e, imgs, count, H, W, overlap, flags, mode, outs, stream ? (cudaStream_t)stream : e->stream);
 }
 
 int emd_set_keep_activations(emd_engine* e, int keep) {
@@ -1400,7 +1482,7 @@ int emd_run_layer(emd_engine* e, const char* name, const float* in, const float*
   if (rres.t >= 0) c.ov.push_back(Override{rres.t, d_res});
   for (int i : idx) {
     cudaError_t r = run_step(c, i);
-    if (r != cudaSuccess) return fail(e, EMD_ECUDA, "step %s: %s", e->steps[i].name.c_str(), cudaGetErrorString(r));
+    if (r != cudaSuccess) return step_error(e, i, r);
   }
   View v; v.ptr = d_out; v.H = to.H; v.W = to.W; v.pitch = rout.C; v.coff = 0; v.C = rout.C;
   rc = download_view(e, v, n, et, to.external, out, s);
@@ -1412,8 +1494,36 @@ int emd_run_layer(emd_engine* e, const char* name, const float* in, const float*
   return rc;
 }
 
-long long emd_kernel_launches(const emd_engine* e) { return e ? e->launches : -1; }
-long long emd_tensor_core_launches(const emd_engine* e) { return e ? e->umma_launches : -1; }
+long long emd_kernel_launches(const emd_engine* e) { return e ? e->cnt.launches : -1; }
+long long emd_tensor_core_launches(const emd_engine* e) { return e ? e->cnt.umma : -1; }
+
+long long emd_counter(const emd_engine* e, const char* name) {
+  if (!e || !name) return -1;
+  static const struct { const char* n; int k; } kinds[] = {
+      {"conv_cuda_core", LK_SIMT}, {"conv_tcgen05_gen1", LK_UMMA_GEN1}, {"conv_fused_taps", LK_FUSED_TAPS}, {"conv_fused_pair", LK_FUSED_PAIR},
+      {"conv_fused_dw", LK_FUSED_DW}, {"final_tcgen05", LK_FINAL_UMMA}, {"final_cuda_core", LK_FINAL_TMA}};
+  const std::string s = name;
+  if (s == "launches") return e->cnt.launches;
+  if (s == "tensor_core_launches") return e->cnt.umma;
+  if (s == "graph_replays") return e->graph_replays;
+  for (auto& k : kinds) if (s == k.n) return e->cnt.kind[k.k];
+  return -1;
+}
+
+int emd_set_option(emd_engine* e, const char* name, long long value) {
+  if (!name) return EMD_EINVAL;
+  if (!tuning_set(name, value)) return fail(e, EMD_EINVAL, "unknown option %s", name);
+  if (e) {
+    if (!strcmp(name, "umma")) e->use_umma = value != 0;
+    drop_graphs(e);    // captured passes hold the old kernel choices
+  }
+  return EMD_OK;
+}
+
+long long emd_get_option(const char* name) {
+  long long v = 0;
+  return (name && tuning_get(name, &v)) ? v : -1;
+}
 long long emd_graph_replays(const emd_engine* e) { return e ? e->graph_replays : -1; }
 
 int emd_set_tensor_cores(emd_engine* e, int on) {

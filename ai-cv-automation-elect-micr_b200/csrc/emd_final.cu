@@ -207,8 +207,7 @@ cudaError_t launch_t(const FinalArgs& a, const CUtensorMap& tmap, int grid, size
 }  // namespace
 
 bool final_umma_supported(const ConvParams& p, int et) {
-  static const bool off = getenv("EMD_DISABLE_FINAL_UMMA") != nullptr;   // A/B switch: the CUDA-core kernel of emd_dw.cu
-  return !off && final_tma_supported(p, et);
+  return tuning().final_umma && final_tma_supported(p, et);   // A/B switch: the CUDA-core kernel of emd_dw.cu
 }
 
 cudaError_t launch_final_umma(const ConvParams& c, float scale, float shift, int et, int num_sms, cudaStream_t s) {

@@ -594,14 +594,9 @@ cudaError_t launch_t(const FusedArgs& a, const CUtensorMap& tin, const OutMaps& 
 
 }  // namespace
 
-static bool g_use_fused = true;
-static bool g_use_pair = true;
-void fused_set_pair(bool on) { g_use_pair = on; }
-void fused_set_enabled(bool on) { g_use_fused = on; }
-
 // dw != nullptr: the GEMM's A operand is the depthwise 3x3 (stride 1, rate 1, SAME) of p.in with weights dw [9][Cin]
 bool fused_supported(const ConvParams& p, int et, const float* dw) {
-  if (!g_use_fused) return false;
+  if (!tuning().fused) return false;
   if (et != ET_BF16 && et != ET_F16) return false;
   if (!p.w16 || p.in_f32 || p.out_f32 || p.clip01) return false;
   if (p.Cout < 8 || p.Cout > kMaxC || (p.Cout & 7) || (p.Cin & 7)) return false;
@@ -678,12 +673,11 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
     // The output ring only needs its third slab where a residual is prefetched into it.
     a.SA = 3; a.SB = 3; a.SH = 6;
     a.ring = a.has_res ? kMaxRing : 2;
-    static const int t_sa = getenv("EMD_DW_SA") ? atoi(getenv("EMD_DW_SA")) : 0, t_sb = getenv("EMD_DW_SB") ? atoi(getenv("EMD_DW_SB")) : 0,
-                     t_sh = getenv("EMD_DW_SH") ? atoi(getenv("EMD_DW_SH")) : 0, t_ring = getenv("EMD_DW_RING") ? atoi(getenv("EMD_DW_RING")) : 0;   // tuning switches
-    if (t_sa) a.SA = t_sa;
-    if (t_sb) a.SB = t_sb;
-    if (t_sh) a.SH = t_sh;
-    if (t_ring) a.ring = t_ring;
+    const Tuning& tn = tuning();
+    if (tn.dw_sa) a.SA = tn.dw_sa;
+    if (tn.dw_sb) a.SB = tn.dw_sb;
+    if (tn.dw_sh) a.SH = tn.dw_sh;
+    if (tn.dw_ring) a.ring = tn.dw_ring;
     while (fused_smem_bytes(a) > (size_t)kSmemLimit) {
       if (a.SH > 4) { --a.SH; continue; }
       if (a.ring == 3 && a.nt.maxrows > 128) { a.ring = 2; continue; }
@@ -696,8 +690,9 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
   } else {
     // CTA pairs for wide N tiles (the GEMM is bound by operand bytes into the SM): half a B stage per CTA
     const int items_pair = (a.m_tiles >> 1) * a.nt.nt * nvar;
-    static const int pair_min_rows = getenv("EMD_PAIR_MIN_ROWS") ? atoi(getenv("EMD_PAIR_MIN_ROWS")) : 128;   // tuning switch
-    a.pair = (g_use_pair && a.nt.maxrows >= pair_min_rows && !(a.m_tiles & 1) && items_pair >= num_sms) ? 1 : 0;
+    const Tuning& tn = tuning();
+    const int min_items = tn.pair_min_items >= 0 ? tn.pair_min_items : num_sms;   // fewer pair items than SMs: single CTAs fill the GPU better
+    a.pair = (tn.pair && a.nt.maxrows >= tn.pair_min_rows && !(a.m_tiles & 1) && items_pair >= 1 && items_pair >= min_items) ? 1 : 0;
     for (int i = 0; i < a.nt.nt && a.pair; ++i)
       if (a.nt.rows[i] & 31) a.pair = 0;                   // N and N/2 stay multiples of 16
     if (a.pair) a.b_stage_bytes = (((a.nt.maxrows >> 1) * 128) + 1023) & ~1023;
@@ -758,9 +753,11 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
   int grid = total_tiles < num_sms ? total_tiles : num_sms;
   if (a.pair) {                          // clusters of 2 walk the pair-item list; an odd cluster count keeps the 4 phases balanced
     int ncl = num_sms >> 1;
-    if (nvar == 4 && !(ncl & 1)) --ncl;
+    const int items_pair = (a.m_tiles >> 1) * a.nt.nt * nvar;
+    if (ncl > items_pair) ncl = items_pair;
+    if (nvar == 4 && ncl > 1 && !(ncl & 1)) --ncl;
     grid = 2 * ncl;
-  } else if (nvar == 4 && !(grid & 3)) --grid;   // a CTA strides the item list by the grid size: keep it odd so every CTA sees all 4 phases (8/4/4/2 k-blocks)
+  } else if (nvar == 4 && grid > 1 && !(grid & 1)) --grid;   // a CTA strides the item list by the grid size: keep it odd so every CTA sees all 4 phases (8/4/4/2 k-blocks)
 #define EMD_DISPATCH(TT)                                                                                                   \
   (a.dw_mode ? (a.has_res ? launch_t<TT, true, true, false>(a, tin, tout, tres, tw, grid, smem, s)                         \
                           : launch_t<TT, true, false, false>(a, tin, tout, tres, tw, grid, smem, s))                       \
@@ -768,6 +765,7 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
                           : launch_t<TT, false, false, true>(a, tin, tout, tres, tw, grid, smem, s))                       \
              : (a.has_res ? launch_t<TT, false, true, false>(a, tin, tout, tres, tw, grid, smem, s)                        \
                           : launch_t<TT, false, false, false>(a, tin, tout, tres, tw, grid, smem, s)))
+  last_launch_kind() = a.dw_mode ? LK_FUSED_DW : (a.pair ? LK_FUSED_PAIR : LK_FUSED_TAPS);
   if (bf16) return EMD_DISPATCH(__nv_bfloat16);
   return EMD_DISPATCH(__half);
 #undef EMD_DISPATCH

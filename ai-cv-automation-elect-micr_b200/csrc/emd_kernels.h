@@ -121,7 +121,6 @@ inline NTiling make_ntiling(int Cout) {
 bool umma_supported(const ConvParams& p, int et);
 cudaError_t launch_conv_umma(const ConvParams& p, int et, int num_sms, cudaStream_t s);
 // packs FP32 [K][Cout] weights into the UMMA tile image; returns bytes needed when dst == nullptr
-void umma_set_tma(bool on);   // A tiles through TMA tensor maps (default) or the cp.async gather only
 size_t umma_pack_weights(const float* w, int ntaps, int Cin, int Cout, int et, void* dst_host);
 
 // emd_fused.cu: second-generation tcgen05 kernel for block-tiled output grids (TMA-store epilogue; optional
@@ -131,14 +130,37 @@ cudaError_t launch_conv_fused(const ConvParams& p, int et, const float* dw, int 
 // the 4 sub-pixel phases of one transposed conv (same input, weights, epilogue; different taps / output offsets) as ONE launch
 bool fused_multi_supported(const ConvParams* ps, int nvar, int et);
 cudaError_t launch_conv_fused_multi(const ConvParams* ps, int nvar, int et, int num_sms, cudaStream_t s);
-void fused_set_enabled(bool on);
-void fused_set_pair(bool on);    // 2-CTA (cta_group::2) GEMM for wide N tiles; default on
 
-// programmatic dependent launch for the kernels that carry griddepcontrol.wait (emd_fused.cu, emd_dw.cu); EMD_DISABLE_PDL=1 = A/B switch
-inline bool pdl_enabled() {
-  static const bool on = !(getenv("EMD_DISABLE_PDL") && getenv("EMD_DISABLE_PDL")[0] == '1');
-  return on;
-}
+// Tuning and A/B switches: ONE struct, filled once per process from the EMD_* environment (emd_tuning.cu) and changed at run
+// time only through emd_set_option (include/emd.h; the tests force kernel variants with it).  Every optimisation that
+// replaced a simpler path keeps that path behind one of these, so a regression can be bisected on the GPU box without a rebuild.
+struct Tuning {
+  int umma = 1;            // EMD_DISABLE_UMMA=1 -> 0: GEMM-class layers of the 16-bit modes on the CUDA-core kernel
+  int fused = 1;           // EMD_DISABLE_FUSED: first-generation tcgen05 kernel (emd_umma.cu) instead of emd_fused.cu
+  int tma = 1;             // EMD_DISABLE_TMA: first-generation kernel without TMA tensor maps
+  int pair = 1;            // EMD_DISABLE_PAIR: no cta_group::2 CTA pairs
+  int final_umma = 1;      // EMD_DISABLE_FINAL_UMMA: final 3x3 conv on the CUDA-core reduction kernel
+  int pdl = 1;             // EMD_DISABLE_PDL: no programmatic dependent launch
+  int graphs = 1;          // EMD_DISABLE_GRAPH: no CUDA-graph replay of whole passes
+  int sliced_io = 1;       // EMD_DISABLE_SLICED_IO: host-buffer passes as the two-chunk pipeline
+  int halves = 1;          // EMD_DISABLE_HALVES: no half-batch head / tail in host-buffer passes
+  int mid_graph = 1;       // EMD_DISABLE_MID_GRAPH: no graph replay of the whole-batch middle section
+  int dw_cols = 1;         // EMD_DISABLE_DW_COLS: depthwise producer with one pixel column per thread (first form)
+  int strict = 0;          // EMD_STRICT=1: a GEMM-class layer of a 16-bit mode that would run on the CUDA-core kernel is an error
+  int graph_max_n = 32;    // EMD_GRAPH_MAX_N: largest batch replayed from a graph
+  int pair_min_rows = 128; // EMD_PAIR_MIN_ROWS: CTA pairs only for N tiles of at least this many columns
+  int pair_min_items = -1; // EMD_PAIR_MIN_ITEMS: CTA pairs only from this many pair items on (-1 = the number of SMs)
+  int io_slices = 0, io_parts = 0;              // EMD_IO_SLICES, EMD_IO_PARTS (0 = defaults)
+  int dw_sa = 0, dw_sb = 0, dw_sh = 0, dw_ring = 0;   // EMD_DW_SA/SB/SH/RING: stage counts of the fused depthwise mode (0 = defaults)
+};
+Tuning& tuning();
+bool tuning_set(const char* name, long long value);      // false: unknown name
+bool tuning_get(const char* name, long long* value);
+inline bool pdl_enabled() { return tuning().pdl != 0; }
+
+// which kernel a conv launcher picked (read by the engine right after the call; per host thread)
+enum LaunchKind { LK_NONE = 0, LK_SIMT, LK_UMMA_GEN1, LK_FUSED_TAPS, LK_FUSED_PAIR, LK_FUSED_DW, LK_FINAL_UMMA, LK_FINAL_TMA, LK_COUNT };
+int& last_launch_kind();
 
 // emd_quality.cu: MSE / Huberised loss / SSIM of image pairs (d_out = 3 doubles per pair, d_partial = quality_partial_bytes)
 size_t quality_partial_bytes(int n, int H, int W);
@@ -152,7 +174,7 @@ cudaError_t launch_normalise_apply(const void* img, int in_f64, size_t n, const 
 cudaError_t launch_gather(const float* img, int H, int W, const int* d_ys, const int* d_xs, int ny, int nx,
                           int crop, float* crops, cudaStream_t s);
 cudaError_t launch_stitch(const float* tiles, const int* d_ys, const int* d_xs, int ny, int nx, int crop, int H,
-                          int W, int clip, double* out, cudaStream_t s);
+                          int W, int clip, void* out /* double*, or float* with out_f32 */, int out_f32, cudaStream_t s);
 size_t minmax_partial_bytes();
 
 }  // namespace emd

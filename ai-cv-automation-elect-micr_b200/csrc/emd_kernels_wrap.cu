@@ -117,9 +117,10 @@ cudaError_t launch_gather(const float* img, int H, int W, const int* d_ys, const
 
 // gather-form overlap average: each output pixel sums its covering tiles in the reference's loop
 // order (i outer, j inner; DEN:666-675) in float64 and divides by the count -- deterministic.
+template <typename TO>
 __global__ void __launch_bounds__(256) stitch_kernel(const float* __restrict__ tiles, const int* __restrict__ ys,
                                                      const int* __restrict__ xs, int ny, int nx, int crop, int H, int W,
-                                                     int clip, double* __restrict__ out) {
+                                                     int clip, TO* __restrict__ out) {
   const size_t total = (size_t)H * W;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(idx % W), r = (int)(idx / W);
@@ -136,14 +137,15 @@ __global__ void __launch_bounds__(256) stitch_kernel(const float* __restrict__ t
     }
     double v = sum / cnt;
     if (clip) v = fmin(fmax(v, 0.0), 1.0);
-    out[idx] = v;
+    out[idx] = (TO)v;     // float output: the float64 average rounded once (round to nearest)
   }
 }
 cudaError_t launch_stitch(const float* tiles, const int* d_ys, const int* d_xs, int ny, int nx, int crop, int H, int W,
-                          int clip, double* out, cudaStream_t s) {
+                          int clip, void* out, int out_f32, cudaStream_t s) {
   const size_t total = (size_t)H * W;
   unsigned blocks = (unsigned)((total + 255) / 256 < (size_t)(148 * 16) ? (total + 255) / 256 : 148 * 16);
-  stitch_kernel<<<blocks, 256, 0, s>>>(tiles, d_ys, d_xs, ny, nx, crop, H, W, clip, out);
+  if (out_f32) stitch_kernel<float><<<blocks, 256, 0, s>>>(tiles, d_ys, d_xs, ny, nx, crop, H, W, clip, reinterpret_cast<float*>(out));
+  else stitch_kernel<double><<<blocks, 256, 0, s>>>(tiles, d_ys, d_xs, ny, nx, crop, H, W, clip, reinterpret_cast<double*>(out));
   return cudaGetLastError();
 }
 

@@ -525,8 +525,6 @@ static bool encode_a_map(const ConvParams& p, int et, CUtensorMap* map) {
   return r == CUDA_SUCCESS;
 }
 
-static bool g_use_tma = true;
-void umma_set_tma(bool on) { g_use_tma = on; }
 
 cudaError_t launch_conv_umma(const ConvParams& p, int et, int num_sms, cudaStream_t s) {
   UmmaArgs a;
@@ -542,7 +540,7 @@ cudaError_t launch_conv_umma(const ConvParams& p, int et, int num_sms, cudaStrea
   a.m_tiles = a.block_mode ? p.N * a.tiles_per_img : (int)((a.M + kBM - 1) / kBM);
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof tmap);
-  a.tma_mode = (g_use_tma && a.block_mode && kTW * p.istride <= 256 && encode_a_map(p, et, &tmap)) ? 1 : 0;
+  a.tma_mode = (tuning().tma && a.block_mode && kTW * p.istride <= 256 && encode_a_map(p, et, &tmap)) ? 1 : 0;
   a.b_stage_bytes = ((a.nt.maxrows * 128) + 1023) & ~1023;
   int stages = 8;
   while (stages > 4 && smem_bytes_for(stages, a.b_stage_bytes) > (size_t)kSmemLimit) --stages;

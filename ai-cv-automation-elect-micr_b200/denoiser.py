@@ -63,13 +63,17 @@ class Denoiser(object):
         weights.py), or None for a fresh graph's initial values (``weights.init_reference_weights``).
     visible_cuda: like the reference, a string put into CUDA_VISIBLE_DEVICES (DEN:591); None leaves
         the environment alone (the reference raises TypeError there, App. D).
-    Extra keyword arguments (not in the reference): device, mode ('bf16' | 'fp16' | 'fp32'),
+    Extra keyword arguments (not in the reference): device, mode -- 'fp16' (default: tcgen05 tensor cores, FP16 operands, FP32
+        accumulation; the mode that meets the 5e-3 parity contract), 'bf16' (same kernels, BF16 operands: opt-in fast mode, 3-4x
+        the rounding error), 'fp32' (CUDA-core validation mode, 1e-5) --,
         cropsize (multiple of 32), max_batch, variant ('A' = misc_py/denoiser-multi-gpu.py:200-540, the canonical
         dense-ASPP graph with the in-graph clip; 'B' = machine_learning/denoiser.py:58-398, the graph of the deployed
         class file: separable ASPP branches with an extra BN/ReLU6, identity image branch, clip in the wrapper).
+        NOTE the default is variant 'A' (the canonical training-script graph BASELINE.json names), while the class file
+        this module replaces builds variant 'B': pass variant='B' to restore a checkpoint trained with that file.
     """
 
-    def __init__(self, checkpoint_loc=None, visible_cuda=None, *, device=0, mode="bf16", cropsize=CROPSIZE,
+    def __init__(self, checkpoint_loc=None, visible_cuda=None, *, device=0, mode="fp16", cropsize=CROPSIZE,
                  max_batch=32, seed=0, variant="A"):
         if visible_cuda is not None:
             os.environ["CUDA_VISIBLE_DEVICES"] = visible_cuda
@@ -125,3 +129,10 @@ class Denoiser(object):
             raise ValueError("denoise expects a 2-D micrograph")
         return self.engine.denoise_image(img, overlap=overlap, preprocess=preprocess, postprocess=postprocess,
                                          mode=self.mode)
+
+    def denoise_many(self, images, preprocess=True, postprocess=True, overlap=80, out_dtype=np.float64):
+        """``denoise`` over a stream of same-sized micrographs (extension; BASELINE.json configs[3]): the same results
+        bit for bit, with copies and wrapper kernels of neighbouring images overlapped with the network passes."""
+        return self.engine.denoise_images([np.asarray(im) if not hasattr(im, "data_ptr") else im for im in images],
+                                          overlap=overlap, preprocess=preprocess, postprocess=postprocess, mode=self.mode,
+                                          out_dtype=out_dtype)

@@ -30,6 +30,41 @@ def _ptr(x):
     raise TypeError(f"unsupported buffer type {type(x)}")
 
 
+def _dtype_name(x):
+    return str(x.dtype).replace("torch.", "")
+
+
+def _dense(x, what, dtypes=("float32",), shape=None):
+    """The C ABI reads raw, dense memory: numpy inputs are converted (a copy only when needed), torch tensors must
+    already be contiguous and of an accepted dtype (a silent copy could land on the wrong device or stream)."""
+    if isinstance(x, np.ndarray):
+        if _dtype_name(x) not in dtypes:
+            x = x.astype(dtypes[0])
+        x = np.ascontiguousarray(x)
+    elif hasattr(x, "data_ptr"):
+        if _dtype_name(x) not in dtypes:
+            raise TypeError(f"{what}: torch dtype {x.dtype} (accepted: {dtypes})")
+        if not x.is_contiguous():
+            raise TypeError(f"{what}: torch tensor must be contiguous")
+    else:
+        raise TypeError(f"{what}: unsupported buffer type {type(x)}")
+    if shape is not None and tuple(x.shape) != tuple(shape):
+        raise ValueError(f"{what}: shape {tuple(x.shape)}, expected {tuple(shape)}")
+    return x
+
+
+def _check_out(out, what, dtype, shape):
+    """A caller-supplied output buffer is written in place: it must already be exactly what the C side assumes."""
+    if _dtype_name(out) != dtype:
+        raise TypeError(f"{what}: dtype {out.dtype}, expected {dtype}")
+    if tuple(out.shape) != tuple(shape):
+        raise ValueError(f"{what}: shape {tuple(out.shape)}, expected {tuple(shape)}")
+    contiguous = out.flags["C_CONTIGUOUS"] if isinstance(out, np.ndarray) else out.is_contiguous()
+    if not contiguous:
+        raise TypeError(f"{what}: must be contiguous")
+    return out
+
+
 class Engine:
     """One GPU + weights + workspace (an ``emd_engine``).  Not thread-safe (emd.h)."""
 
@@ -60,11 +95,14 @@ class Engine:
         self._check(self.lib.emd_load_weights(self.h, C.c_char_p(blob), len(blob)), "emd_load_weights")
 
     # -- network ---------------------------------------------------------------------------
-    def forward(self, crops, out=None, mode="bf16", stream=None):
+    def forward(self, crops, out=None, mode="fp16", stream=None):
         """crops [n,S,S] float32 (numpy, or torch host/CUDA tensor) -> [n,S,S] float32."""
         n = int(crops.shape[0])
-        if tuple(crops.shape[1:3]) != (self.S, self.S):
+        if len(crops.shape) != 3 or tuple(crops.shape[1:3]) != (self.S, self.S):
             raise ValueError(f"crops must be [n,{self.S},{self.S}], got {tuple(crops.shape)}")
+        crops = _dense(crops, "crops")
+        if out is not None:
+            _check_out(out, "out", "float32", (n, self.S, self.S))
         if out is None:
             if isinstance(crops, np.ndarray):
                 out = np.empty((n, self.S, self.S), np.float32)
@@ -148,41 +186,80 @@ class Engine:
             b = np.ascontiguousarray(b, np.float32)
         if tuple(a.shape) != tuple(b.shape) or len(a.shape) not in (2, 3):
             raise ValueError(f"quality: shapes {tuple(a.shape)} and {tuple(b.shape)}")
+        a, b = _dense(a, "quality: a"), _dense(b, "quality: b")
         n = 1 if len(a.shape) == 2 else int(a.shape[0])
         H, W = int(a.shape[-2]), int(a.shape[-1])
         out = np.empty((n, 3), np.float64)
         self._check(self.lib.emd_quality(self.h, _ptr(a), _ptr(b), n, H, W, _ptr(out), _stream_for(a, None)), "emd_quality")
         return out
 
-    def denoise_image(self, img, overlap=80, preprocess=True, postprocess=True, mode="bf16", out=None):
-        """Whole micrograph in one call: normalise -> tile -> batched forward -> stitch (emd_denoise_image)."""
-        is_np = isinstance(img, np.ndarray)
-        if is_np:
-            if img.dtype not in (np.float32, np.float64):
-                img = img.astype(np.float32)
-            if img.dtype == np.float64 and not preprocess:
-                img = img.astype(np.float32)
-            img = np.ascontiguousarray(img)
-            f64 = img.dtype == np.float64
-        else:
-            import torch
-            f64 = img.dtype == torch.float64
+    def _image_args(self, img, preprocess):
+        if len(img.shape) != 2:
+            raise ValueError(f"expected a 2-D micrograph, got shape {tuple(img.shape)}")
+        if isinstance(img, np.ndarray) and img.dtype == np.float64 and not preprocess:
+            img = img.astype(np.float32)
+        return _dense(img, "img", ("float32", "float64") if preprocess else ("float32",))
+
+    def _image_out(self, img, out, H, W, out_dtype):
+        name = np.dtype(out_dtype).name
+        if name not in ("float32", "float64"):
+            raise TypeError(f"out_dtype {out_dtype}: float64 (the reference's accumulator type) or float32")
+        if out is not None:
+            return _check_out(out, "out", name, (H, W))
+        if isinstance(img, np.ndarray):
+            return np.empty((H, W), out_dtype)
+        import torch
+        return torch.empty((H, W), dtype=getattr(torch, name), device=img.device)
+
+    def _image_flags(self, preprocess, postprocess, f64, out):
+        return (_lib.EMD_FLAG_PREPROCESS if preprocess else 0) | (_lib.EMD_FLAG_POSTPROCESS if postprocess else 0) \
+            | (_lib.EMD_FLAG_INPUT_F64 if f64 else 0) | (_lib.EMD_FLAG_OUTPUT_F32 if _dtype_name(out) == "float32" else 0)
+
+    def denoise_image(self, img, overlap=80, preprocess=True, postprocess=True, mode="fp16", out=None, out_dtype=np.float64):
+        """Whole micrograph in one call: normalise -> tile -> batched forward -> stitch (emd_denoise_image).
+        out_dtype: float64 like the reference's accumulators (DEN:658), or float32 (the same values rounded once; half the
+        download)."""
+        img = self._image_args(img, preprocess)
         H, W = int(img.shape[0]), int(img.shape[1])
         if H < self.S or W < self.S:
             raise ValueError(f"image {H}x{W} is smaller than the {self.S}x{self.S} crop")
         if not 0 <= overlap < self.S:
             raise ValueError(f"overlap {overlap} outside [0,{self.S})")
-        if out is None:
-            if is_np:
-                out = np.empty((H, W), np.float64)
-            else:
-                import torch
-                out = torch.empty((H, W), dtype=torch.float64, device=img.device)
-        flags = (_lib.EMD_FLAG_PREPROCESS if preprocess else 0) | (_lib.EMD_FLAG_POSTPROCESS if postprocess else 0) \
-            | (_lib.EMD_FLAG_INPUT_F64 if f64 else 0)
+        out = self._image_out(img, out, H, W, out_dtype)
+        flags = self._image_flags(preprocess, postprocess, _dtype_name(img) == "float64", out)
         self._check(self.lib.emd_denoise_image(self.h, _ptr(img), H, W, overlap, flags, MODES[mode], _ptr(out),
                                                _stream_for(img, None)), "emd_denoise_image")
         return out
+
+    def denoise_images(self, imgs, overlap=80, preprocess=True, postprocess=True, mode="fp16", outs=None, out_dtype=np.float64,
+                       stream=None):
+        """A stream of same-sized micrographs (emd_denoise_stream): bit-identical to denoise_image on each, with the
+        next image's upload / normalise / tile gather and the previous image's stitch / download under the current
+        image's network pass.  Pinned host buffers (torch ``pin_memory``) are what makes the copies overlap."""
+        imgs = [self._image_args(im, preprocess) for im in imgs]
+        if not imgs:
+            return []
+        H, W = int(imgs[0].shape[0]), int(imgs[0].shape[1])
+        kind = _dtype_name(imgs[0])
+        for im in imgs:
+            if tuple(im.shape) != (H, W) or _dtype_name(im) != kind:
+                raise ValueError("denoise_images: all micrographs of one call must have the same shape and dtype")
+        if H < self.S or W < self.S:
+            raise ValueError(f"image {H}x{W} is smaller than the {self.S}x{self.S} crop")
+        if not 0 <= overlap < self.S:
+            raise ValueError(f"overlap {overlap} outside [0,{self.S})")
+        if outs is None:
+            outs = [None] * len(imgs)
+        if len(outs) != len(imgs):
+            raise ValueError("denoise_images: one output buffer per image")
+        outs = [self._image_out(im, o, H, W, out_dtype) for im, o in zip(imgs, outs)]
+        flags = self._image_flags(preprocess, postprocess, kind == "float64", outs[0])
+        n = len(imgs)
+        ins_a = (C.c_void_p * n)(*[_ptr(im) for im in imgs])
+        outs_a = (C.c_void_p * n)(*[_ptr(o) for o in outs])
+        self._check(self.lib.emd_denoise_stream(self.h, ins_a, n, H, W, overlap, flags, MODES[mode], outs_a,
+                                                _stream_for(imgs[0], stream)), "emd_denoise_stream")
+        return outs
 
     # -- measurement ---------------------------------------------------------------------------
     @property
@@ -196,6 +273,20 @@ class Engine:
     @property
     def graph_replays(self):
         return int(self.lib.emd_graph_replays(self.h))
+
+    def counter(self, name):
+        """Launch counters by name (emd_counter): e.g. 'conv_fused_pair', 'conv_fused_dw', 'conv_cuda_core'."""
+        v = int(self.lib.emd_counter(self.h, name.encode()))
+        if v < 0:
+            raise KeyError(name)
+        return v
+
+    def set_option(self, name, value):
+        """Tuning / A-B switches (emd_set_option; process-wide, see include/emd.h)."""
+        self._check(self.lib.emd_set_option(self.h, name.encode(), int(value)), f"emd_set_option({name})")
+
+    def get_option(self, name):
+        return int(self.lib.emd_get_option(name.encode()))
 
     def set_tensor_cores(self, on=True):
         self._check(self.lib.emd_set_tensor_cores(self.h, int(on)), "emd_set_tensor_cores")

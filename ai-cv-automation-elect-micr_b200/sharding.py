@@ -20,12 +20,13 @@ def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_items, world))
 
 
-def run_sharded(items: Sequence, fn: Callable, rank: int, world: int, group=None, gather: bool = True):
+def run_sharded(items: Sequence, fn: Callable, rank: int, world: int, group=None, gather: bool = True, precomputed=None):
     """Apply ``fn`` to the items this rank owns; with ``gather`` every rank gets the full result list in item order.
 
-    ``fn(item)`` is e.g. ``Denoiser.denoise``.  ``group`` is a torch.distributed process group (None = default)."""
+    ``fn(item)`` is e.g. ``Denoiser.denoise``.  ``group`` is a torch.distributed process group (None = default).
+    ``precomputed``: {item index: result} for this rank's items when the caller has already produced them in one batch."""
     mine = shard_indices(len(items), rank, world)
-    local = [(k, fn(items[k])) for k in mine]
+    local = [(k, precomputed[k] if precomputed is not None else fn(items[k])) for k in mine]
     if not gather or world == 1:
         out = [None] * len(items)
         for k, r in local:
@@ -43,5 +44,13 @@ def run_sharded(items: Sequence, fn: Callable, rank: int, world: int, group=None
 
 def denoise_stream(denoiser, images: Sequence, rank: int = 0, world: int = 1, group=None, gather: bool = True, **kw):
     """BASELINE.json config 4: a stream of micrographs, image k on GPU k % world; each rank tiles, infers and stitches
-    its own images end to end (``Denoiser.denoise``), results gathered on the host."""
+    its own images end to end, results gathered on the host.  A rank's images go through ``Denoiser.denoise_many`` (copies
+    of neighbouring images overlapped with the network passes) when they share one shape, else one ``Denoiser.denoise``
+    call each -- the results are bit-identical either way, and identical to a single-GPU run."""
+    mine = shard_indices(len(images), rank, world)
+    shapes = {tuple(getattr(images[k], "shape", ())) for k in mine}
+    if len(mine) > 1 and len(shapes) == 1 and hasattr(denoiser, "denoise_many"):
+        results = denoiser.denoise_many([images[k] for k in mine], **kw)
+        by_index = dict(zip(mine, results))
+        return run_sharded(images, None, rank, world, group, gather, precomputed=by_index)
     return run_sharded(images, lambda img: denoiser.denoise(img, **kw), rank, world, group, gather)

@@ -5,14 +5,19 @@
 
 A "step" is one pass of the hot path (the atrous Xception denoiser forward) over one batch of
 synthetic 512x512 crops.  At N=1 the workload is BASELINE.json configs[1]: batch 32 of 512x512
-crops on one B200 in the BF16 tensor-core mode.  N>1 (launched with torch.distributed.run, one rank
-per GPU) shards independent crops across GPUs -- no data-path collective, weak scaling.
+crops on one B200 in the tensor-core mode that meets the parity contract (FP16 operands, FP32
+accumulation; `dtype`).  N>1 (launched with torch.distributed.run, one rank per GPU) shards independent
+crops across GPUs -- no data-path collective, weak scaling.
 
 One JSON line on stdout (rank 0).  `value` = crops/s with the inputs resident in HBM; `e2e` = the
 same metric through the public API with pinned HOST buffers (H2D and D2H inside the timed region);
 `roofline` describes the dominant kernel, measured live with CUDA events; `cpu_baseline` is the
 oracle (PyTorch-CPU restatement of the reference TF graph -- TensorFlow cannot run here) timed on
-this box's host cores on a bounded sample.
+this box's host cores on a bounded sample.  `configs` carries the other BASELINE.json configs:
+ms per 2048x2048 micrograph (GPU host-to-host / device-resident / in a stream, and the CPU port's 25
+sequential batch-1 passes + stitch, DEN:666-677), the 96x96 x 4096 small-image path, batch-1 latency,
+the other arithmetic modes; `stream_4096` is configs[3]: a stream of 4096x4096 micrographs, image k on
+rank k % N, with a hash check that the sharded outputs equal a single GPU's bit for bit.
 
 --impl reference times that CPU restatement alone, with all host threads, batch 1 per pass like
 the reference's sess.run loop (DEN:646-647, 666-675).
@@ -20,6 +25,7 @@ the reference's sess.run loop (DEN:646-647, 666-675).
 from __future__ import annotations
 
 import argparse
+import hashlib
 import importlib
 import json
 import os
@@ -54,6 +60,20 @@ def synthetic_crops(n, s, seed=1234):
         mn, mx = lq.min(), lq.max()
         out[i] = (lq - mn) / (mx - mn) if mx > mn else 0.5
     return out
+
+
+def synthetic_micrograph(size, seed=1234):
+    """One low-dose micrograph of size x size as raw Poisson counts (float32, NOT normalised: the wrapper's preprocess
+    does that, DEN:655-656): smooth positive field x dose (gen_lq / get_scale, DMG:785-799)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:size, 0:size].astype(np.float32) / size
+    f = np.full((size, size), 0.1, np.float32)
+    for _ in range(24):
+        cy, cx, sg, a = rng.random(), rng.random(), 0.02 + 0.2 * rng.random(), rng.random()
+        f += a * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * sg * sg))
+    lam = 25.0 + rng.exponential(75.0)
+    return rng.poisson(f / f.mean() * lam).astype(np.float32)
 
 
 def peaks():
@@ -115,25 +135,57 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def time_cpu_oracle(n_pass, s=CROP, seed=0):
-    """Bounded CPU sample: n_pass batch-1 passes of the oracle after one warm-up.  Returns crops/s."""
+WORKLOAD = (f"batch {BATCH} of {CROP}x{CROP} synthetic crops per GPU per step through the atrous Xception denoiser "
+            f"(variant A, random-init weights), BASELINE.json configs[1]")
+
+
+def config_dict(n_sets):
+    """Identical for both arms (the driver compares them): what is computed, not how."""
+    return {"workload": WORKLOAD, "batch_per_gpu": BATCH, "crop": CROP,
+            "l2": f"{n_sets} rotating input sets ({n_sets * BATCH * CROP * CROP * 4 / 1e6:.0f} MB > 126 MB L2); activations per step "
+                  "(~1 GB per crop) far exceed L2; no explicit flush"}
+
+
+def n_input_sets():
+    return 5
+
+
+def cpu_reference_leg(n_crops, s=CROP, stitch_2048=False):
+    """The reference's CPU path through its PyTorch restatement (oracle/), all host threads, batch 1 per pass like the
+    reference's sess.run loop (DEN:646-647).  Returns (crops/s from the median pass, threads, per-pass seconds, and -- with
+    stitch_2048 -- ms for one 2048x2048 micrograph = 25 sequential passes + normalise / tile / stitch, DEN:653-682)."""
+    import numpy as np
     import torch
+    from oracle import wrapper as W
     from oracle.net import OracleNet
     emd = importlib.import_module("ai-cv-automation-elect-micr_b200")
     torch.set_num_threads(os.cpu_count() or 1)
-    net = OracleNet(emd.weights.init_reference_weights(seed), s)
-    x = synthetic_crops(1, s)
-    net.forward(x)
+    net = OracleNet(emd.weights.init_reference_weights(0), s)
+    net.forward(synthetic_crops(1, s))          # warm-up
     ts = []
-    for _ in range(n_pass):
+    ms_2048 = None
+    if stitch_2048:
+        img = synthetic_micrograph(2048, seed=5)
+
+        def one(c):
+            t0 = time.perf_counter()
+            r = net.forward(c)
+            ts.append(time.perf_counter() - t0)
+            return r
         t0 = time.perf_counter()
-        net.forward(x)
-        ts.append(time.perf_counter() - t0)
-    ts.sort()
-    return 1.0 / ts[len(ts) // 2], torch.get_num_threads()
+        W.denoise(img, lambda crops: np.concatenate([one(crops[i:i + 1]) for i in range(len(crops))]), overlap=80, crop=s)
+        ms_2048 = (time.perf_counter() - t0) * 1e3
+    else:
+        x = synthetic_crops(1, s)
+        for _ in range(n_crops):
+            t0 = time.perf_counter()
+            net.forward(x)
+            ts.append(time.perf_counter() - t0)
+    med = sorted(ts)[len(ts) // 2]
+    return 1.0 / med, torch.get_num_threads(), ts, ms_2048
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads."""
     if rank != 0:
         return
@@ -159,38 +211,41 @@ def run_reference(args, rank):
     dt = time.perf_counter() - t1
     v = done / dt
     cores = torch.get_num_threads()
-    sample = f"{done} batch-1 passes over one 512x512 crop (the reference runs one sess.run per crop, DEN:646-647)"
+    sample = (f"{done} batch-1 passes over one {CROP}x{CROP} crop of the workload's batch per timed step: the reference runs one "
+              f"sess.run per crop (DEN:646-647), so its crops/s does not depend on the batch; PyTorch-CPU restatement of the "
+              f"reference TF graph (TensorFlow is not installable here), FP32")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / done, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"batch {BATCH} of {CROP}x{CROP} synthetic crops per GPU per step through the atrous Xception "
-                               f"denoiser (variant A, random-init weights), BASELINE.json configs[1]",
-                   "batch_per_gpu": BATCH, "crop": CROP, "mode": "f32",
-                   "sample_per_step": "1 of the batch's crops per timed step (the reference runs one sess.run per crop, "
-                                      "DEN:646-647, so crops/s does not depend on the batch); PyTorch-CPU restatement of the "
-                                      "reference TF graph, TensorFlow is not installable here"},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(n_input_sets()),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 
+def sha(arrays):
+    h = hashlib.blake2b(digest_size=16)
+    for a in arrays:
+        h.update(a.tobytes() if hasattr(a, "tobytes") else a.numpy().tobytes())
+    return h.hexdigest()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp16", "fp32"])
-    ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--crop", type=int, default=CROP)
+    ap.add_argument("--mode", default="fp16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (2048^2, 96^2, stream, modes)")
+    ap.add_argument("--stream-images", type=int, default=8, help="4096x4096 micrographs per rank in the stream config")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
         return
 
     import numpy as np
@@ -203,16 +258,18 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    S, B = args.crop, args.batch
+    S, B = CROP, BATCH
     eng = emd.Engine(device=local, cropsize=S, max_batch=B)
-    eng.load_weights(emd.weights.pack(emd.weights.init_reference_weights(0)))
+    eng.set_option("strict", 1)     # a GEMM-class layer with no tensor-core kernel is an error here, never a silent CUDA-core launch
+    blob = emd.weights.pack(emd.weights.init_reference_weights(0))
+    eng.load_weights(blob)
     tstream = torch.cuda.Stream()  # the engine launches on this stream; the timing events are recorded on it
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
 
     # rotating input sets so the inputs alone exceed the 126 MB L2 (the activations, ~1 GB per crop, do anyway)
-    n_sets = max(2, int(np.ceil(140e6 / (B * S * S * 4))))
-    host_sets = [torch.from_numpy(synthetic_crops(B, S, seed=1234 + 97 * rank + i)).pin_memory() for i in range(min(n_sets, 5))]
+    n_sets = n_input_sets()
+    host_sets = [torch.from_numpy(synthetic_crops(B, S, seed=1234 + 97 * rank + i)).pin_memory() for i in range(n_sets)]
     dev_sets = [h.cuda() for h in host_sets]
     d_out = torch.empty((B, S, S), dtype=torch.float32, device="cuda")
     h_out = torch.empty((B, S, S), dtype=torch.float32).pin_memory()
@@ -222,7 +279,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, units_per_step=1.0):
+        """W untimed calls, then exactly `steps` calls between CUDA events on the launching stream, barrier + synchronize on
+        both sides, max over ranks.  Returns (ms total, kernel launches in the timed region summed over ranks)."""
         for i in range(warmup):
             fn(i)
         barrier()
@@ -245,30 +304,49 @@ def main():
         barrier()
         return ms, launches
 
+    dev_pass = lambda i: eng.forward(dev_sets[i % n_sets], out=d_out, mode=args.mode, stream=stream)
+    host_pass = lambda i: eng.forward(host_sets[i % n_sets], out=h_out, mode=args.mode, stream=stream)
+
     sampler = ClockSampler(local)
     sampler.start()
-    ms, launches = timed(lambda i: eng.forward(dev_sets[i % len(dev_sets)], out=d_out, mode=args.mode, stream=stream),
-                         args.steps, args.warmup)
-    clocks = sampler.stop()
+    # pre-heat: ~2 s of the same passes before the W warm-up steps, so the K timed steps (0.2 s) run at the clocks a long job
+    # settles at under the 1 kW cap, not at the boost clocks of an idle GPU
+    t_heat = time.perf_counter()
+    heat = 0
+    while time.perf_counter() - t_heat < 2.0:
+        for i in range(8):
+            dev_pass(heat + i)
+        torch.cuda.synchronize()
+        heat += 8
+    c0 = {k: eng.counter(k) for k in ("conv_cuda_core", "conv_fused_pair", "conv_fused_taps", "conv_fused_dw", "conv_tcgen05_gen1",
+                                      "final_tcgen05", "tensor_core_launches", "launches")}
+    ms, launches = timed(dev_pass, args.steps, args.warmup)
+    per_pass = {k: (eng.counter(k) - c0[k]) / (args.steps + args.warmup) for k in c0}
     value = world * B * args.steps / (ms * 1e-3)
+    if args.mode != "fp32":     # the benchmarked step ran on the kernels it claims: no CUDA-core conv, no first-generation kernel
+        assert per_pass["conv_cuda_core"] == 0 and per_pass["conv_tcgen05_gen1"] == 0, per_pass
+        assert per_pass["conv_fused_pair"] >= 39 and per_pass["conv_fused_dw"] >= 1 and per_pass["final_tcgen05"] == 1, per_pass
 
     # end to end through the public API with pinned host buffers (H2D + D2H inside the timed region)
-    ms_e2e, _ = timed(lambda i: eng.forward(host_sets[i % len(host_sets)], out=h_out, mode=args.mode, stream=stream),
-                      args.steps, 1)
+    ms_e2e, _ = timed(host_pass, args.steps, 2)
+    clocks = sampler.stop()
     e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": B * S * S * 4, "d2h_bytes_per_step": B * S * S * 4}
 
-    # per-kernel device times (CUDA events around every step of the schedule, separate pass)
     out = {}
+    pk = peaks()
     if rank == 0:
-        pk = peaks()
+        # per-kernel device times (CUDA events around every step of the schedule, separate passes, mean of 3)
         eng.set_profile(True)
-        eng.forward(dev_sets[0], out=d_out, mode=args.mode, stream=stream)
-        info = eng.step_info()
+        acc = None
+        for r in range(3):
+            eng.forward(dev_sets[r % n_sets], out=d_out, mode=args.mode, stream=stream)
+            cur = eng.step_info()
+            acc = cur if acc is None else [(a[0], a[1] + c[1], a[2], a[3], a[4]) for a, c in zip(acc, cur)]
+        info = [(n_, m_ / 3, f_, b_, l_) for n_, m_, f_, b_, l_ in acc]
         eng.set_profile(False)
         tot_ms = sum(i[1] for i in info)
-        # dominant kernel = the step with the largest device time; a step is one kernel launch, except the
-        # transposed convs (4 sub-pixel phase launches of the same kernel): per-launch figures divide by `launches`
+        # dominant kernel = the step with the largest device time (one launch per step on this path)
         name, kms, fl, by, nl = max(info, key=lambda i: i[1])
         nl = max(nl, 1)
         fl, by = fl * B / nl, by * B / nl          # algorithmic work of ONE launch (whole batch)
@@ -291,27 +369,143 @@ def main():
         t_roof = sum(max(f * B / (pk["tflops"] * 1e12), b * B / (pk["hbm_gbs"] * 1e9)) for _, _, f, b, n_ in info if n_ > 0)
         roof["network_roofline_ms"] = t_roof * 1e3
         roof["network_frac"] = t_roof * 1e3 / (ms / args.steps)
+        roof["survey_ideal_fusion_frac"] = (B / 4780.0 * 1e3) / (ms / args.steps)   # 4780 crops/s per B200 with every depthwise fused
         top = sorted(info, key=lambda i: -i[1])[:8]
         roof["top_steps_ms"] = {i[0]: round(i[1], 3) for i in top}
         out["roofline"] = roof
-        if not args.no_cpu_baseline and world == 1:   # the CPU leg is reported at N=1 only (the other ranks would wait for it)
-            n_pass = 12   # ~10 s of CPU work on the box's host cores
-            v, cores = time_cpu_oracle(n_pass, S)
+        out["kernels_per_pass"] = per_pass
+
+    configs = {}
+    stream_cfg = None
+    if not args.no_configs:
+        # ---- BASELINE configs[3]: a stream of 4096x4096 micrographs, image k -> rank k % N (sharding.denoise_stream's rule) ----
+        M = args.stream_images
+        bases = [torch.from_numpy(synthetic_micrograph(4096, seed=40 + j)).pin_memory() for j in range(4)]
+        total = M * world
+        mine = emd.sharding.shard_indices(total, rank, world)
+        imgs = [bases[k % len(bases)] for k in mine]
+        outs = [torch.empty((4096, 4096), dtype=torch.float32).pin_memory() for _ in range(M)]
+        seng = emd.Engine(device=local, cropsize=S, max_batch=25)      # 100 crops per image = 4 balanced passes of 25
+        seng.set_option("strict", 1)
+        seng.load_weights(blob)
+        run_stream = lambda ims: seng.denoise_images(ims, overlap=80, mode=args.mode, outs=outs[:len(ims)], out_dtype=np.float32, stream=stream)
+        hashes = [sha([o]) for o in run_stream(imgs)]                  # warm-up pass (graph capture, buffers) + its hashes
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_stream(imgs)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_stream = e0.elapsed_time(e1)
+        hashes2 = [sha([o]) for o in outs[:len(imgs)]]
+        if world > 1:
+            t = torch.tensor([ms_stream], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_stream = float(t.item())
+        # bit-identity: a second pass gives the same bits, and (N > 1) rank 0 recomputes every other rank's images alone on its
+        # own GPU and compares the hashes -- the N-GPU result is the single-GPU result
+        identical = hashes == hashes2
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, (mine, hashes2))
+            if rank == 0:
+                for r_mine, r_hashes in gathered[1:]:
+                    res = run_stream([bases[k % len(bases)] for k in r_mine])
+                    identical = identical and [sha([o]) for o in res] == r_hashes
+        stream_cfg = {"workload": f"{M} micrographs of 4096x4096 per GPU, 100 overlapping 512x512 crops each (overlap 80), image k on rank k % N; "
+                                  "pinned float32 in, float32 out",
+                      "images": total, "images_per_s": total / (ms_stream * 1e-3), "crops_per_s": total * 100 / (ms_stream * 1e-3),
+                      "ms_per_image_per_gpu": ms_stream / M,
+                      "bit_identical_to_single_gpu": bool(identical) if rank == 0 else None}
+        del seng
+
+    if rank == 0 and not args.no_configs:
+        # ---- configs[2]: one 2048x2048 micrograph, 25 crops ----
+        meng = emd.Engine(device=local, cropsize=S, max_batch=25)
+        meng.set_option("strict", 1)
+        meng.load_weights(blob)
+        img = synthetic_micrograph(2048, seed=5)
+        himg = torch.from_numpy(img).pin_memory()
+        hout64 = torch.empty((2048, 2048), dtype=torch.float64).pin_memory()
+        hout32 = torch.empty((2048, 2048), dtype=torch.float32).pin_memory()
+        dimg = himg.cuda()
+        dres = torch.empty((2048, 2048), dtype=torch.float64, device="cuda")
+
+        def wall(fn, reps=10, warm=3):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / reps * 1e3
+        m = {"crops": 25, "overlap": 80,
+             "gpu_e2e": wall(lambda: meng.denoise_image(himg, out=hout64, mode=args.mode)),
+             "gpu_e2e_f32_out": wall(lambda: meng.denoise_image(himg, out=hout32, mode=args.mode, out_dtype=np.float32)),
+             "gpu_device": wall(lambda: meng.denoise_image(dimg, out=dres, mode=args.mode)),
+             "note": "ms, host wall clock around synchronous calls: gpu_e2e = pinned float32 image in, float64 image out on the host "
+                     "(the reference's types, DEN:658); gpu_device = image and result resident in HBM; gpu_stream = per image in a stream "
+                     "of 8 (copies of neighbouring images under the network passes, emd_denoise_stream)"}
+        s_in = [himg] * 8
+        s_out = [torch.empty((2048, 2048), dtype=torch.float32).pin_memory() for _ in range(8)]
+        m["gpu_stream"] = wall(lambda: meng.denoise_images(s_in, outs=s_out, mode=args.mode, out_dtype=np.float32), reps=3, warm=1) / 8
+        configs["ms_per_2048_micrograph"] = m
+        # configs[0]-like latency: one crop, batch 1
+        d1 = dev_sets[0][:1].contiguous()
+        o1 = torch.empty_like(d1)
+        configs["ms_per_512_crop_batch1"] = wall(lambda: meng.forward(d1, out=o1, mode=args.mode), reps=20, warm=5)
+        del meng
+        # the other arithmetic modes on configs[1]
+        modes = {}
+        for mode, steps in (("bf16", 5), ("fp16", 5), ("fp32", 2)):
+            if mode == args.mode:
+                modes[mode] = B * args.steps / (ms * 1e-3)
+                continue
+            t_ms, _ = timed(lambda i, mode=mode: eng.forward(dev_sets[i % n_sets], out=d_out, mode=mode, stream=stream), steps, 2)
+            modes[mode] = B * steps / (t_ms * 1e-3)
+        configs["crops_per_s_by_mode"] = modes
+        # ---- configs[4]: 96x96 crops at batch 4096 (small_scans shape) ----
+        del eng
+        torch.cuda.empty_cache()
+        e96 = emd.Engine(device=local, cropsize=96, max_batch=4096)
+        e96.load_weights(blob)
+        x96 = torch.from_numpy(np.random.default_rng(96).random((4096, 96, 96)).astype(np.float32)).cuda()
+        y96 = torch.empty_like(x96)
+        ms96 = wall(lambda: e96.forward(x96, out=y96, mode=args.mode, stream=stream), reps=3, warm=2)
+        l0 = e96.kernel_launches
+        e96.forward(x96, out=y96, mode=args.mode, stream=stream)
+        torch.cuda.synchronize()
+        configs["crops_96x96_batch4096"] = {"crops_per_s": 4096 / ms96 * 1e3, "ms_per_pass": ms96, "kernel_launches_per_pass": e96.kernel_launches - l0,
+                                            "roofline_crops_per_s": 143000, "frac": 4096 / ms96 * 1e3 / 143000}
+        del e96
+        if not args.no_cpu_baseline and world == 1:
+            # the CPU leg: ONE 2048x2048 micrograph through the oracle port = 25 sequential batch-1 passes + stitch (DEN:666-677);
+            # its median pass also gives the CPU crops/s
+            v, cores, ts, ms2048 = cpu_reference_leg(25, S, stitch_2048=True)
+            configs["ms_per_2048_micrograph"]["cpu_port"] = ms2048
+            configs["ms_per_2048_micrograph"]["cpu_cores"] = cores
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                   "sample": f"median of {n_pass} batch-1 passes of the PyTorch-CPU oracle over one "
-                                             f"{S}x{S} crop (1 warm-up)"}
+                                   "sample": f"median of the 25 batch-1 passes of the PyTorch-CPU oracle over the 512x512 crops of one "
+                                             f"2048x2048 micrograph (1 warm-up pass; the whole micrograph incl. stitch took {ms2048:.0f} ms)"}
+    elif rank == 0 and not args.no_cpu_baseline and world == 1:
+        v, cores, ts, _ = cpu_reference_leg(12, S)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"median of 12 batch-1 passes of the PyTorch-CPU oracle over one {S}x{S} crop (1 warm-up)"}
+
+    if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.mode, "data": "synthetic",
-            "config": {"workload": f"batch {B} of {S}x{S} synthetic crops per GPU per step through the atrous Xception "
-                                   f"denoiser (variant A, random-init weights), BASELINE.json configs[1]",
-                       "batch_per_gpu": B, "crop": S, "mode": args.mode,
-                       "l2": f"{len(dev_sets)} rotating input sets ({len(dev_sets) * B * S * S * 4 / 1e6:.0f} MB > 126 MB L2); "
-                             "activations per step far exceed L2; no explicit flush"},
+            "dtype": args.mode, "data": "synthetic", "config": config_dict(n_sets),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "pre_heat": f"{heat} untimed passes (~2 s) before the warm-up steps: the timed steps run at steady-state clocks",
         }
         line.update(out)
+        if configs:
+            line["configs"] = configs
+        if stream_cfg:
+            line["stream_4096"] = stream_cfg
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -51,6 +51,7 @@ extern "C" {
 #define EMD_FLAG_PREPROCESS   1   /* DEN:655-656 (repaired): NaN/Inf->0.5 then scale0to1 */
 #define EMD_FLAG_POSTPROCESS  2   /* DEN:679-680: clip(0,1) */
 #define EMD_FLAG_INPUT_F64    4   /* img is const double* (np.random.rand in DEN:708 is float64) */
+#define EMD_FLAG_OUTPUT_F32   8   /* out is float* (the float64 overlap average rounded once); default double* like the reference's np.zeros accumulators (DEN:658) */
 
 typedef struct emd_engine emd_engine;
 
@@ -98,9 +99,16 @@ int emd_stitch(emd_engine* e, const float* tiles, const int* ys, const int* xs, 
 
 /* Replaces Denoiser.denoise (DEN:653-682 == TMP:3-32) end to end on one GPU: normalise -> tile ->
  * batched forward -> overlap-averaged stitch -> clip.  img [H,W] f32 (or f64 with
- * EMD_FLAG_INPUT_F64), out [H,W] f64. */
+ * EMD_FLAG_INPUT_F64), out [H,W] f64 (f32 with EMD_FLAG_OUTPUT_F32). */
 int emd_denoise_image(emd_engine* e, const void* img, int H, int W, int overlap, int flags,
-                      int mode, double* out, void* stream);
+                      int mode, void* out, void* stream);
+
+/* A stream of `count` micrographs of one size (BASELINE.json configs[3]; the reference calls Denoiser.denoise once per
+ * image, DEN:653): the same result as emd_denoise_image on each, bit for bit, but image i+1's upload + normalise + tile
+ * gather and image i-1's stitch + download run on their own streams under image i's network pass (two staging slots).
+ * imgs[i] / outs[i]: host (pinned for real overlap) or device pointers, formats as in emd_denoise_image. */
+int emd_denoise_stream(emd_engine* e, const void* const* imgs, int count, int H, int W, int overlap,
+                       int flags, int mode, void* const* outs, void* stream);
 
 /* Image-quality metrics of the reference's training / evaluation code (misc_py/denoiser-multi-gpu.py) between n pairs of
  * [H,W] f32 images a[i], b[i] (host or device; H, W >= 11): out[3*i + 0] = mean squared error (DMG:772),
@@ -121,6 +129,18 @@ int emd_run_layer(emd_engine* e, const char* name, const float* in, const float*
 /* number of kernels this engine has launched since creation; of those, tcgen05 (UMMA) kernels */
 long long emd_kernel_launches(const emd_engine* e);
 long long emd_tensor_core_launches(const emd_engine* e);
+/* other counters by name: "launches", "tensor_core_launches", "graph_replays", and conv launches by the kernel that ran them:
+ * "conv_fused_pair" (emd_fused.cu, cta_group::2 CTA pairs), "conv_fused_taps", "conv_fused_dw" (depthwise computed inside the GEMM
+ * kernel), "conv_tcgen05_gen1" (emd_umma.cu), "conv_cuda_core" (FP32 mode, or a 16-bit shape no tensor-core kernel supports),
+ * "final_tcgen05", "final_cuda_core".  -1 = unknown name.  The parity tests assert with these that the kernel under test ran. */
+long long emd_counter(const emd_engine* e, const char* name);
+/* Tuning / A-B switches (csrc/emd_kernels.h, struct Tuning): process-wide, initialised once from the EMD_* environment, changed
+ * by name here; `e` (may be NULL) drops its captured graphs so the change takes effect.  Names: umma, fused, tma, pair,
+ * final_umma, pdl, graphs, sliced_io, halves, mid_graph, dw_cols, strict, graph_max_n, pair_min_rows, pair_min_items,
+ * io_slices, io_parts, dw_sa, dw_sb, dw_sh, dw_ring.  strict = 1: a GEMM-class layer of a 16-bit mode that no tensor-core
+ * kernel supports is an error (EMD_ESTATE) instead of a silent CUDA-core launch. */
+int       emd_set_option(emd_engine* e, const char* name, long long value);
+long long emd_get_option(const char* name);   /* -1 = unknown name */
 /* passes replayed from a captured CUDA graph (batches <= 32 from their third pass on; EMD_DISABLE_GRAPH=1 turns it off, EMD_GRAPH_MAX_N changes the limit) */
 long long emd_graph_replays(const emd_engine* e);
 /* on = 0: the 16-bit modes run their GEMM-class layers on the CUDA-core kernel with the same

@@ -199,12 +199,19 @@ class OracleNet:
         # BF16-storage emulation (error-budget experiments for the tensor-core path): round GEMM
         # operands (activations as stored, depthwise output, weights) to bf16, accumulate in FP32.
         self.emulate_bf16 = False
+        self.emulate_dtype = None      # torch.bfloat16 / torch.float16: same emulation with that storage type
         self.trunk_fp32 = False
+        self.q_only = None             # None = every source; else a set of tags (see _q)
 
     _PRE_SUM = ("_strided", "cnn4_2", "deconv2_1", "deconv1_1", "deconv0_1")
 
-    def _q(self, x):
-        return x.to(torch.bfloat16).to(self.dtype) if self.emulate_bf16 else x
+    def _q(self, x, tag="act"):
+        """Round to the emulated 16-bit storage type.  tag: what is being stored ('dw' = depthwise result handed to
+        the GEMM, 'w' = GEMM weights, 'act' = an activation tensor); ``q_only`` restricts the emulation to some tags."""
+        dt = self.emulate_dtype or (torch.bfloat16 if self.emulate_bf16 else None)
+        if dt is None or (self.q_only is not None and tag not in self.q_only):
+            return x
+        return x.to(dt).to(self.dtype)
 
     def _qt(self, x):
         """The 728-wide trunk: bf16 storage unless ``trunk_fp32`` (then only GEMM/dw inputs are rounded)."""
@@ -242,24 +249,24 @@ class OracleNet:
     def sep(self, x, name, stride=1, rate=1):
         """strided_conv_block: dw3x3 -> pw1x1 (no bias) -> BN -> BN -> ReLU6 (DMG:250-276)."""
         y = depthwise3x3(x, self.p[f"{name}/dw"], stride, rate)
-        y = self._q(y)
+        y = self._q(y, "dw")
         if self.collect:
             self.acts[f"{name}:dw"] = y.permute(0, 2, 3, 1).contiguous().numpy()
-        y = self._rescale(conv2d(y, self._q(self.p[f"{name}/pw"]), None), f"{name}/pw")
+        y = self._rescale(conv2d(y, self._q(self.p[f"{name}/pw"], "w"), None), f"{name}/pw")
         y = self._bn(y, f"{name}/bn1")
         y = self._bn(y, f"{name}/bn2")
         return self._keep(name, self._qout(name, relu6(y)))
 
     def conv(self, x, name, stride=1, rate=1):
         """conv_block_not_sep / residual_conv / ASPP convs: conv + bias -> BN -> ReLU6 (DMG:225-238, 363-373)."""
-        y = self._rescale(conv2d(x, self._q(self.p[f"{name}/kernel"]), None, stride, rate), f"{name}/kernel")
+        y = self._rescale(conv2d(x, self._q(self.p[f"{name}/kernel"], "w"), None, stride, rate), f"{name}/kernel")
         y = self._bn(y + self.p[f"{name}/bias"].view(1, -1, 1, 1), f"{name}/bn")
         return self._keep(name, self._qout(name, relu6(y)))
 
     def deconv(self, x, name):
         """deconv_block (DMG:278-289)."""
         zero = torch.zeros_like(self.p[f"{name}/bias"])
-        y = self._rescale(conv2d_transpose_s2(x, self._q(self.p[f"{name}/tkernel"]), zero), f"{name}/tkernel")
+        y = self._rescale(conv2d_transpose_s2(x, self._q(self.p[f"{name}/tkernel"], "w"), zero), f"{name}/tkernel")
         y = self._bn(y + self.p[f"{name}/bias"].view(1, -1, 1, 1), f"{name}/bn")
         return self._keep(name, self._qout(name, relu6(y)))
 
@@ -328,6 +335,34 @@ class OracleNet:
                 y = torch.clamp(y, 0.0, 1.0)  # DMG:534-538
             y = self._keep("output", y)
         return y.reshape(-1, self.S, self.S).numpy()
+
+    def run_layer(self, name, x, res=None):
+        """One layer of the schedule on an NHWC numpy input (``res``: NHWC tensor added after the activation, the
+        post-ReLU6 adds of DMG:408/423/438/453/466/390/504/516/528) -> NHWC numpy.  The per-layer parity tests feed
+        the same seeded tensors to this and to the engine's ``emd_run_layer``."""
+        t = torch.as_tensor(np.asarray(x)).to(self.dtype).permute(0, 3, 1, 2).contiguous()
+        with torch.no_grad():
+            if name.startswith("residual") and not name.endswith("_d"):
+                y = self.conv(t, name, stride=2)                       # residual_conv, DMG:363-373
+            elif name.endswith("_strided"):
+                y = self.sep(t, name, stride=2)
+            elif name in ("deconv2to1", "deconv1to0"):
+                y = self.deconv(t, name)
+            elif name.startswith("aspp_r") and self.variant == "A":
+                y = self.conv(t, name, rate=int(name[6:]))
+            elif name in ("aspp_1x1", "aspp_pellet") or name.endswith("_d"):
+                y = self.conv(t, name)
+            elif name == "final":
+                y = self.conv(t, name)
+                if self.variant == "A":
+                    y = torch.clamp(y, 0.0, 1.0)
+            elif name == "upsample4":
+                y = resize_bilinear_legacy(t, self.S // 4, self.S // 4)
+            else:
+                y = self.sep(t, name)                                   # every other layer is a strided_conv_block, stride 1
+            if res is not None:
+                y = y + torch.as_tensor(np.asarray(res)).to(self.dtype).permute(0, 3, 1, 2)
+        return y.permute(0, 2, 3, 1).contiguous().numpy()
 
     def export_params(self):
         return {k: v.to(torch.float32).numpy().copy() for k, v in self.p.items()}

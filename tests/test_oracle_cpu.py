@@ -2,6 +2,7 @@
 (SURVEY.md App. A), and the committed golden fixtures.  The reference has no tests for this path."""
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -117,6 +118,28 @@ def test_network_golden_s64():
     # every activation is O(1) with W1 (that is what W1 is for, App. E.3)
     for k in ("mid5_2", "aspp_r18", "dec0"):
         assert 0.1 < net.acts[k].std() < 5.0
+
+
+def test_known_answer_vectors_s96():
+    """SURVEY 8(c) pin 3: committed known-answer vectors for a 96x96 W1 case -- sum, sum of squares and 32 sampled values
+    of EVERY named activation of the graph, plus the whole output.  (Weights are re-derived by calibration, so the
+    comparison carries a small tolerance; a changed op, padding, concat order or fold shows up as O(1).)"""
+    sys.path.insert(0, GOLD)
+    from make_golden import kat_positions, kat_s96_inputs
+    g = np.load(os.path.join(GOLD, "net_s96_kat.npz"))
+    crops = kat_s96_inputs()
+    net = O.OracleNet(make_w1(crops, seed=96), 96, dtype=torch.float64)
+    net.collect = True
+    out = net.forward(crops)
+    assert rel_l2(out, g["out"]) < 1e-4
+    assert len(g["layer_names"]) == 146
+    for name, sums, samp, shape in zip(g["layer_names"], g["sums"], g["samples"], g["shapes"]):
+        a = net.acts[str(name)]
+        assert tuple(a.shape) == tuple(shape), name
+        assert abs(a.sum() - sums[0]) <= 1e-4 * (abs(sums[0]) + np.sqrt(sums[1] * a.size) * 1e-2), name
+        assert abs((a.astype(np.float64) ** 2).sum() - sums[1]) <= 2e-4 * sums[1] + 1e-12, name
+        got = a.reshape(-1)[kat_positions(str(name), a.size)]
+        assert np.linalg.norm(got - samp) <= 2e-4 * np.linalg.norm(samp) + 1e-6, name
 
 
 def test_f64_switch_agrees():

@@ -28,6 +28,33 @@ def _worker(rank, world, port, q):
 
     out = sharding.run_sharded(images, fake_denoise, rank, world)
     ok = all(np.array_equal(o, 1.0 - i) for o, i in zip(out, images))
+
+    class FakeDenoiser:      # the stream form: a rank's same-sized images go through ONE denoise_many call (emd_denoise_stream)
+        batches = []
+
+        def denoise(self, img, **kw):
+            raise AssertionError("same-sized images must take the batched route")
+
+        def denoise_many(self, imgs, **kw):
+            self.batches.append(len(imgs))
+            return [1.0 - i * kw.get("overlap", 1) for i in imgs]
+
+    fd = FakeDenoiser()
+    out2 = sharding.denoise_stream(fd, images, rank, world, overlap=2)
+    ok = ok and all(np.array_equal(o, 1.0 - 2 * i) for o, i in zip(out2, images)) and fd.batches == [len(sharding.shard_indices(7, rank, world))]
+    ragged = images[:2] + [rng.random((4, 4)), rng.random((4, 4))]   # each rank owns one 6x5 and one 4x4: one denoise call per image
+    seen = []
+
+    class PerImage:
+        def denoise(self, img, **kw):
+            seen.append(img.shape)
+            return img + 1.0
+
+        def denoise_many(self, imgs, **kw):
+            raise AssertionError("mixed sizes cannot be batched")
+
+    out3 = sharding.denoise_stream(PerImage(), ragged, rank, world)
+    ok = ok and all(np.array_equal(o, i + 1.0) for o, i in zip(out3, ragged))
     q.put((rank, ok, len(calls), sharding.shard_indices(len(images), rank, world)))
     dist.barrier()
     dist.destroy_process_group()

@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--checkpoint", default=None)
     ap.add_argument("--variant", default="A", choices=["A", "B"])
     ap.add_argument("--overlap", type=int, default=80)
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--mode", default="fp16", choices=["bf16", "fp16", "fp32"])
     a = ap.parse_args()
     import denoiser
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
