@@ -49,8 +49,12 @@ struct FusedArgs {
   ConvParams p;
   NTiling nt;
   int dw_mode;
+  int dw_cols;               // dw mode: depthwise thread mapping (1 = 2 channels x 4 columns x 4 rows, 0 = 4 channels x 1 column x 8 rows)
   int SA, SB, SH, ring;      // taps mode: SA stages of (A + B), SB == SA, SH == 0
   int b_stage_bytes, nchunks, w_kblocks, m_tiles, tiles_x, tiles_per_img;
+  // tile geometry: an M tile is a box of bw x bh pixels from each of bn consecutive images (<= 128 pixels; 16 x 8 x 1 wherever the
+  // map tiles that way, whole-row boxes over several images for the small maps of small crops); tiles_per_img = tiles per image GROUP
+  int bw, bh, bn, a_tile_bytes;
   int tmem_cols, acc_stride;
   int has_res;
   // pair mode (taps mode, wide N tiles): 2-CTA clusters; tcgen05.mma.cta_group::2 with M = 256 (each CTA's 128 pixels)
@@ -66,6 +70,12 @@ struct FusedArgs {
   int b_res;                 // taps mode: every B block of the launch stays in shared memory, loaded once per CTA (block = tap*nchunks + chunk)
   FastDiv d_nt, d_tpi, d_tx, d_chunks;   // by nt.nt, tiles_per_img, tiles_x, nchunks
   const float* dw_w;         // [9][Cin] FP32, tap-major (dw mode)
+  // depthwise through global memory (kDwG: pair-mode GEMM whose A operand is produced during the launch by the math warps)
+  const void* dwg_in;        // depthwise input, first channel of the view
+  void* dwg_out;             // depthwise result = the GEMM's A tensor (p.in), first channel of the view
+  int dwg_in_pitch, dwg_out_pitch, dwg_H, dwg_W;
+  int* dwg_ready;            // [m_tiles] counters, zeroed before the launch; [m_tiles] = fault flag
+  int dwg_target;            // warps per item x chunks
 };
 
 template <typename T> struct Cv;
@@ -101,11 +111,12 @@ template <> struct Cv<__half> {
 };
 
 __device__ __forceinline__ void tile_coords(const FusedArgs& a, int mt, int& n_img, int& y0, int& x0) {
-  n_img = (int)fdiv((uint32_t)mt, a.d_tpi);
-  const int rem = mt - n_img * a.tiles_per_img;
+  const int grp = (int)fdiv((uint32_t)mt, a.d_tpi);
+  const int rem = mt - grp * a.tiles_per_img;
   const int by = (int)fdiv((uint32_t)rem, a.d_tx);
-  y0 = by * kTH;
-  x0 = (rem - by * a.tiles_x) * kTW;
+  n_img = grp * a.bn;
+  y0 = by * a.bh;
+  x0 = (rem - by * a.tiles_x) * a.bw;
 }
 
 // position in a ring of n pipeline stages plus the mbarrier phase parity of the current pass
@@ -159,8 +170,8 @@ __device__ __forceinline__ void epi_half(const uint32_t (&v)[32], const float* _
 
 struct OutMaps { CUtensorMap m[4]; };   // output tensor map per variant
 
-template <typename T, bool kDw, bool kRes, bool kPair>
-__global__ void __launch_bounds__(kDw ? base_threads(true) + kMathThreads : base_threads(false), 1)
+template <typename T, bool kDw, bool kRes, bool kPair, bool kDwG = false>
+__global__ void __launch_bounds__((kDw || kDwG) ? base_threads(true) + kMathThreads : base_threads(false), 1)
 fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ CUtensorMap tmap_in,
                   const __grid_constant__ OutMaps tmaps_out, const __grid_constant__ CUtensorMap tmap_res,
                   const __grid_constant__ CUtensorMap tmap_w) {
@@ -314,6 +325,20 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
         const char* tbase = wbase + (size_t)a.nt.rows_before[ntile] * a.w_kblocks * 128;
         int n_img, y0, x0;
         tile_coords(a, mt, n_img, y0, x0);
+        if constexpr (kDwG) {
+          // the A operand of this M tile is the depthwise result that the math warps (of any CTA) write to global memory during
+          // this launch: wait until all of its (chunk, warp) parts are published, then order the async proxy (TMA) after them
+          if (elect_one()) {
+            const int* flag = a.dwg_ready + mt;
+            int spins = 0;
+            while (ld_acquire_gpu(flag) < a.dwg_target) {
+              __nanosleep(100);
+              if (++spins > (1 << 22)) { atomicExch(a.dwg_ready + a.m_tiles, 1); break; }   // never hang the GPU: flag the fault, read what is there
+            }
+            fence_proxy_async_all();
+          }
+          __syncwarp();
+        }
         {
           const int xb = x0 * p.istride, yb = y0 * p.istride;
           if (a.b_res && tile == first && elect_one()) {   // first tile of this CTA: bring in every weight block, once
@@ -332,13 +357,13 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
                 if constexpr (kPair) {
                   // both CTAs' copies complete on the LEADER's full barrier; each CTA brings its own A tile and its half of B's rows
                   // (the weight box always has maxrows/2 rows; for a narrower last N tile the surplus rows are never read)
-                  if (crank == 0) mbar_arrive_expect_tx(bar, 2u * ((uint32_t)(a.nt.maxrows >> 1) * 128u + (uint32_t)kAStageBytes));
+                  if (crank == 0) mbar_arrive_expect_tx(bar, 2u * ((uint32_t)(a.nt.maxrows >> 1) * 128u + (uint32_t)a.a_tile_bytes));
                   tma_load_4d_2sm(sA + (uint32_t)ra.idx * kAStageBytes, &tmap_in, c * kBK, xt, yt, n_img, bar);
                   const int half = a.nt.rows[ntile] >> 1;
                   tma_load_2d_2sm(sB + (uint32_t)ra.idx * a.b_stage_bytes, &tmap_w, 0,
                                   (a.b_row0[ntile] + (a.v_wrow[var][t] * a.nchunks + c) * a.nt.rows[ntile] + (int)crank * half) >> 2, bar);
                 } else {
-                  mbar_arrive_expect_tx(bar, (a.b_res ? 0u : bytes) + (uint32_t)kAStageBytes);
+                  mbar_arrive_expect_tx(bar, (a.b_res ? 0u : bytes) + (uint32_t)a.a_tile_bytes);
                   tma_load_4d(sA + (uint32_t)ra.idx * kAStageBytes, &tmap_in, c * kBK, xt, yt, n_img, bar);
                   if (!a.b_res) bulk_g2s(sB + (uint32_t)ra.idx * a.b_stage_bytes, wsrc, bytes, bar);
                 }
@@ -416,7 +441,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
         split(pf_tile, mt, ntile, var);
         int n_img, y0, x0;
         tile_coords(a, mt, n_img, y0, x0);
-        mbar_arrive_expect_tx(bar_rfull + 8u * pf_buf, kSlabBytes);
+        mbar_arrive_expect_tx(bar_rfull + 8u * pf_buf, (uint32_t)a.a_tile_bytes);   // a 64-channel slab of the tile's pixels
         tma_load_4d(sO + (uint32_t)pf_buf * kSlabBytes, &tmap_res, a.nt.n0[ntile] + pf_slab * 64, x0, y0, n_img, bar_rfull + 8u * pf_buf);
         if (++pf_slab * 64 >= a.nt.rows[ntile]) { pf_slab = 0; pf_tile += step; }
       }
@@ -439,19 +464,20 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
       const int nslabs = (n + 63) >> 6;
       // this warp converts the 32-column half `my_half` of every 64-column slab; the accumulator read of slab j+1 is in
       // flight while slab j is converted and stored (the epilogue, not the MMA, paces the output-heavy layers)
-      constexpr int kVB = kDw ? 1 : 2;           // dw mode runs at 72 registers per thread: no room for a second buffer
+      constexpr bool kMath = kDw || kDwG;        // kernels with depthwise math warps run at 72 registers per thread: no room for a second buffer
+      constexpr int kVB = kMath ? 1 : 2;
       uint32_t v[kVB][32];
       const int cbase = my_half * 32;
-      if (!kDw && cbase < n) tmem_ld32(taddr + (uint32_t)cbase, v[0]);
+      if (!kMath && cbase < n) tmem_ld32(taddr + (uint32_t)cbase, v[0]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (j >= nslabs) break;
         const int buf = rq.idx;
         uint8_t* srow = g_stage + (size_t)buf * kSlabBytes + row_off;
         const int c0 = j * 64 + cbase;           // column within the N tile
-        if (kDw && c0 < n) tmem_ld32(taddr + (uint32_t)c0, v[0]);
+        if (kMath && c0 < n) tmem_ld32(taddr + (uint32_t)c0, v[0]);
         tmem_ld_wait();
-        if (!kDw && j + 1 < nslabs && c0 + 64 < n) tmem_ld32(taddr + (uint32_t)(c0 + 64), v[(j + 1) % kVB]);
+        if (!kMath && j + 1 < nslabs && c0 + 64 < n) tmem_ld32(taddr + (uint32_t)(c0 + 64), v[(j + 1) % kVB]);
         if (j == nslabs - 1) {                   // this warp's last read of the accumulator is done: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -485,14 +511,75 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
     // 16 lanes read one 128-byte halo pixel per LDS.64, the window slides down the column in registers.
     const int tm = threadIdx.x - kBaseThreads;           // 0..511
     const int grp = tm >> 8, tg = tm & 255;
+    const int items = ((total_tiles - first + step - 1) / step) * a.nchunks;   // this CTA's (tile, chunk) items
+    Ring rh(grp, SH), ra(grp, SA);
+    int c = grp % a.nchunks;
+    int cur_c = -1;
+    if (a.dw_cols) {
+      // Thread = 2 channels x 4 pixel columns x 4 rows.  A warp's 32 lanes are the 32 channel pairs of one halo pixel, so every
+      // LDS.32 / STS.32 is one conflict-free 128-byte wavefront, and a loaded + unpacked halo value feeds up to 9 outputs of this
+      // thread: 36 loads and 72 unpacks per 32 outputs, against 30 two-wavefront LDS.64 and 120 unpacks with one column per
+      // thread.  Row-accumulate form: halo row j adds into output rows j-2 .. j, so at most three output rows are live.
+      const int cp = tg & 31, sub = tg >> 5;
+      const int x0 = (sub & 3) * 4, y0 = (sub >> 2) * 4;
+      const uint32_t h_thread = (uint32_t)((y0 * kHaloW + x0) * (kBK * 2) + cp * 4);
+      uint32_t a_off[4];                               // this thread's bytes within an A-stage row, per output column (swizzle by column)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a_off[i] = (uint32_t)((x0 + i) * 128 + ((((cp >> 2) ^ ((x0 + i) & 7)) << 4) + (cp & 3) * 4));
+      float2 w[9];
+      for (int it = grp; it < items; it += 2) {
+        if (c != cur_c) {
+          cur_c = c;
+          const int ch = c * kBK + cp * 2;
+          const bool ch_ok = ch < p.Cin;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) w[t] = ch_ok ? __ldg(reinterpret_cast<const float2*>(a.dw_w + t * p.Cin + ch)) : make_float2(0.f, 0.f);
+        }
+        mbar_wait(bar_hfull + 8u * rh.idx, rh.phase);
+        mbar_wait(bar_aempty + 8u * ra.idx, ra.phase ^ 1u);
+        const uint8_t* hb = g_halo + (size_t)rh.idx * kHaloBytes + h_thread;
+        uint8_t* ab = smem + (size_t)ra.idx * kAStageBytes + (size_t)y0 * kTW * 128;
+        float2 acc[3][4];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {                  // halo rows y0 - 1 + j
+          float2 x[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) x[i] = Cv<T>::up(*reinterpret_cast<const uint32_t*>(hb + (j * kHaloW + i) * (kBK * 2)));
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {             // this halo row is tap row ky of output row j - ky
+            const int r = j - ky;
+            if (r < 0 || r > 3) continue;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float2& d = acc[r % 3][i];
+              d = ky == 0 ? fmul2(x[i], w[0]) : ffma2(x[i], w[ky * 3], d);
+              d = ffma2(x[i + 1], w[ky * 3 + 1], d);
+              d = ffma2(x[i + 2], w[ky * 3 + 2], d);
+            }
+          }
+          if (j >= 2) {                                // output row j - 2 is complete
+            const int r = j - 2;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint32_t*>(ab + r * kTW * 128 + a_off[i]) = Cv<T>::pack(acc[r % 3][i].x, acc[r % 3][i].y);
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar_afull + 8u * ra.idx);
+          mbar_arrive(bar_hempty + 8u * rh.idx);
+        }
+        rh.advance(2); ra.advance(2);
+        c += 2;
+        if (c >= a.nchunks) c -= a.nchunks;
+        if (c >= a.nchunks) c -= a.nchunks;
+      }
+    } else {
     const int cq = tg & 15, col = tg >> 4;
     const uint32_t a_thread = (uint32_t)col * 128u + (uint32_t)((((cq >> 1) ^ (col & 7)) << 4) + (cq & 1) * 8);
     const uint32_t h_thread = (uint32_t)col * (kBK * 2) + (uint32_t)cq * 8;
     float2 w[9][2];
-    int cur_c = -1;
-    const int items = ((total_tiles - first + step - 1) / step) * a.nchunks;   // this CTA's (tile, chunk) items
-    Ring rh(grp, SH), ra(grp, SA);
-    int c = grp % a.nchunks;
     for (int it = grp; it < items; it += 2) {
       if (c != cur_c) {
         cur_c = c;
@@ -541,6 +628,92 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
       if (c >= a.nchunks) c -= a.nchunks;
       if (c >= a.nchunks) c -= a.nchunks;
     }
+    }
+  }
+
+  if constexpr (kDwG) {
+    if (warp >= kBaseThreads / 32) {
+      // ===================== depthwise math warps, result through global memory (L2) =====================
+      // The 728-wide separable blocks have three N tiles; computing the depthwise in the A-operand producer would repeat it per
+      // N tile.  Here the 16 math warps of every CTA compute it ONCE per (M tile, 64-channel chunk) item -- straight from the
+      // previous layer's output in global memory to a global scratch tensor that stays in L2 -- and publish a per-M-tile
+      // counter; the TMA producers of the GEMM (above) wait for the counter of the tile they are about to load.  The GEMM is
+      // bound by the tensor pipe / operand ingress, so the CUDA-core depthwise hides under it: one launch per separable block
+      // instead of two, and no serial depthwise phase.  Items are walked in M-tile order by all CTAs, the GEMM walks the same
+      // order, and the math warps wait for nothing inside the launch: no cycle, no deadlock.
+      // Thread = 2 channels x 1 pixel column x 8 rows; a warp = the 32 channel pairs of one column (every LDG.32 / STG.32 of the
+      // warp is one 128-byte line), all 16 math warps of the CTA work on the same (M tile, chunk) item, so the three columns a
+      // warp reads are shared with its neighbours through L1.  The loads come straight from global memory (L2): what hides their
+      // latency is depth -- kAhead halo rows (3 loads each) in flight per thread -- which the small register footprint of the
+      // one-column mapping pays for (these warps share the SM with the GEMM's epilogue at 72 registers per thread).
+      constexpr int kAhead = 4;
+      const int tm = threadIdx.x - kBaseThreads;               // 0..511
+      const int cp = tm & 31, x0 = tm >> 5;                     // channel pair, pixel column of the tile
+      const int n_items = a.m_tiles * a.nchunks;
+      const int H = a.dwg_H, W = a.dwg_W;
+      const int ipitch = a.dwg_in_pitch >> 1, opitch = a.dwg_out_pitch >> 1;       // in 32-bit words (channel pairs)
+      const uint32_t* gin = reinterpret_cast<const uint32_t*>(a.dwg_in);
+      uint32_t* gout = reinterpret_cast<uint32_t*>(a.dwg_out);
+      int cur_c = -1;
+      float2 w[9];
+      for (int it = (int)blockIdx.x; it < n_items; it += (int)gridDim.x) {
+        const int mt = (int)fdiv((uint32_t)it, a.d_chunks), c = it - mt * a.nchunks;
+        const int cw = c * (kBK / 2) + cp;                            // channel pair of this lane
+        const bool ch_ok = 2 * cw < p.Cin;
+        if (c != cur_c) {
+          cur_c = c;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) w[t] = ch_ok ? __ldg(reinterpret_cast<const float2*>(a.dw_w + t * p.Cin + 2 * cw)) : make_float2(0.f, 0.f);
+        }
+        int n_img, ty, tx;
+        tile_coords(a, mt, n_img, ty, tx);
+        const int xb = tx + x0 - 1;                                   // leftmost halo column
+        const int irow0 = (n_img * H + ty - 1) * W;                   // pixel index of halo row 0, column 0 (guarded by y_ok when outside)
+        const int opix0 = (n_img * H + ty) * W + tx + x0;
+        bool x_ok[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) x_ok[i] = ch_ok && xb + i >= 0 && xb + i < W;
+        uint32_t raw[kAhead][3];
+        auto load_row = [&](int j) {
+          const int y = ty - 1 + j;
+          const bool y_ok = y >= 0 && y < H;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            uint32_t v = 0u;
+            if (y_ok && x_ok[i]) v = __ldg(gin + (size_t)(unsigned)((irow0 + j * W + xb + i) * ipitch + cw));
+            raw[j % kAhead][i] = v;
+          }
+        };
+#pragma unroll
+        for (int j = 0; j < kAhead; ++j) load_row(j);
+        float2 acc[3];
+#pragma unroll
+        for (int j = 0; j < kTH + 2; ++j) {                           // halo rows ty - 1 + j
+          float2 x[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) x[i] = Cv<T>::up(raw[j % kAhead][i]);
+          if (j + kAhead < kTH + 2) load_row(j + kAhead);             // refill the slot just consumed
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int r = j - ky;
+            if (r < 0 || r >= kTH) continue;
+            float2& d = acc[r % 3];
+            d = ky == 0 ? fmul2(x[0], w[0]) : ffma2(x[0], w[ky * 3], d);
+            d = ffma2(x[1], w[ky * 3 + 1], d);
+            d = ffma2(x[2], w[ky * 3 + 2], d);
+          }
+          if (j >= 2 && ch_ok) {
+            const int r = j - 2;
+            gout[(size_t)(unsigned)((opix0 + r * W) * opitch + cw)] = Cv<T>::pack(acc[r % 3].x, acc[r % 3].y);
+          }
+        }
+        __syncwarp();                                               // orders the other lanes' stores before lane 0's release
+        if (lane == 0) {
+          __threadfence();
+          atomicAdd(a.dwg_ready + mt, 1);
+        }
+      }
+    }
   }
 
   // teardown: everyone done with TMEM, then the allocating warp frees it
@@ -559,18 +732,18 @@ size_t fused_smem_bytes(const FusedArgs& a) {
          (size_t)a.SH * kHaloBytes + 2 * kMaxC * sizeof(float) + (6 * kMaxStages + 4 + kMaxRing) * 8 + 16;
 }
 
-template <typename T, bool kDw, bool kRes, bool kPair>
+template <typename T, bool kDw, bool kRes, bool kPair, bool kDwG = false>
 cudaError_t launch_t(const FusedArgs& a, const CUtensorMap& tin, const OutMaps& tout, const CUtensorMap& tres, const CUtensorMap& tw,
                      int grid, size_t smem, cudaStream_t s) {
   static thread_local int attr_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (attr_dev != dev) {
-    cudaError_t r = cudaFuncSetAttribute(fused_conv_kernel<T, kDw, kRes, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaError_t r = cudaFuncSetAttribute(fused_conv_kernel<T, kDw, kRes, kPair, kDwG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (r != cudaSuccess) return r;
     attr_dev = dev;
   }
-  const int block = kDw ? base_threads(true) + kMathThreads : base_threads(false);
+  const int block = (kDw || kDwG) ? base_threads(true) + kMathThreads : base_threads(false);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)block);
@@ -589,10 +762,26 @@ cudaError_t launch_t(const FusedArgs& a, const CUtensorMap& tin, const OutMaps& 
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, fused_conv_kernel<T, kDw, kRes, kPair>, a, tin, tout, tres, tw);
+  return cudaLaunchKernelEx(&cfg, fused_conv_kernel<T, kDw, kRes, kPair, kDwG>, a, tin, tout, tres, tw);
 }
 
 }  // namespace
+
+// Tile geometry of an output grid of N maps of MH x MW pixels: 16 x 8 pixel blocks of one image where the map tiles that way
+// (the shape the depthwise producer and the fused trunk work on); else whole rows -- bh rows from each of bn consecutive images,
+// chosen to fill the 128-row M tile best (6 x 6 maps of 96 x 96 crops: 3 rows x 7 images = 126 pixels; 24 x 24: 1 x 5 = 120).
+static bool pick_tile(int MH, int MW, int N, int* bw, int* bh, int* bn) {
+  if (MH % kTH == 0 && MW % kTW == 0) { *bw = kTW; *bh = kTH; *bn = 1; return true; }
+  if (MW > kBM || MW < 1) return false;
+  double best = 0;
+  for (int h = 1; h <= MH && h * MW <= kBM; ++h)
+    for (int n = 1; n * h * MW <= kBM && n <= 16 && n <= (N > 1 ? N : 1); ++n) {
+      const double tiles = (double)((N + n - 1) / n) * ((MH + h - 1) / h);
+      const double eff = (double)N * MH * MW / (tiles * kBM);
+      if (eff > best + 1e-9) { best = eff; *bw = MW; *bh = h; *bn = n; }
+    }
+  return best > 0;
+}
 
 // dw != nullptr: the GEMM's A operand is the depthwise 3x3 (stride 1, rate 1, SAME) of p.in with weights dw [9][Cin]
 bool fused_supported(const ConvParams& p, int et, const float* dw) {
@@ -602,8 +791,10 @@ bool fused_supported(const ConvParams& p, int et, const float* dw) {
   if (p.Cout < 8 || p.Cout > kMaxC || (p.Cout & 7) || (p.Cin & 7)) return false;
   if ((p.in.pitch & 7) || (p.in.coff & 7) || (p.out.pitch & 7) || (p.out.coff & 7)) return false;
   if (p.res.ptr && ((p.res.pitch & 7) || (p.res.coff & 7))) return false;
-  if (p.MH % kTH || p.MW % kTW) return false;
-  if (kTW * p.istride > 256) return false;
+  int bw, bh, bn;
+  if (!pick_tile(p.MH, p.MW, p.N, &bw, &bh, &bn)) return false;
+  if (bw * p.istride > 256 || bh * p.istride > 256) return false;
+  if (dw && (bw != kTW || bh != kTH || bn != 1)) return false;   // the depthwise producer works on 8 x 16 pixel tiles
   const NTiling nt = make_ntiling(p.Cout);
   if (nt.nt > kMaxNTiles) return false;
   if (nt.nt > 1 && (nt.rows[0] & 63)) return false;  // a 64-channel output slab must not straddle two N tiles
@@ -630,16 +821,43 @@ bool fused_multi_supported(const ConvParams* ps, int nvar, int et) {
   return true;
 }
 
-static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const float* dw, int num_sms, cudaStream_t s);
+static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const float* dw, const DwGlobal* g, int num_sms, cudaStream_t s);
 
 cudaError_t launch_conv_fused(const ConvParams& p, int et, const float* dw, int num_sms, cudaStream_t s) {
-  return launch_impl(&p, 1, et, dw, num_sms, s);
+  return launch_impl(&p, 1, et, dw, nullptr, num_sms, s);
 }
 cudaError_t launch_conv_fused_multi(const ConvParams* ps, int nvar, int et, int num_sms, cudaStream_t s) {
-  return launch_impl(ps, nvar, et, nullptr, num_sms, s);
+  return launch_impl(ps, nvar, et, nullptr, nullptr, num_sms, s);
 }
 
-static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const float* dw, int num_sms, cudaStream_t s) {
+// CTA pairs (cta_group::2) for wide N tiles -- the GEMM is bound by operand bytes into the SM, and a pair holds half a B stage
+// per CTA -- when there are enough pair items to fill the GPU
+static bool want_pair(int m_tiles, const NTiling& nt, int nvar, int num_sms) {
+  const Tuning& tn = tuning();
+  const int items_pair = (m_tiles >> 1) * nt.nt * nvar;
+  const int min_items = tn.pair_min_items >= 0 ? tn.pair_min_items : num_sms;   // fewer pair items than SMs: single CTAs fill the GPU better
+  if (!(tn.pair && nt.maxrows >= tn.pair_min_rows && !(m_tiles & 1) && items_pair >= 1 && items_pair >= min_items)) return false;
+  for (int i = 0; i < nt.nt; ++i)
+    if (nt.rows[i] & 31) return false;                   // N and N/2 stay multiples of 16
+  return true;
+}
+
+// A stride-1 separable block with SEVERAL N tiles (the 728-wide trunk): the depthwise is computed once per M tile by math warps
+// that run beside the pair-mode GEMM and hand their result over through global memory (kDwG in the kernel)
+bool fused_dwg_supported(const ConvParams& p, int et, const DwGlobal& g, int num_sms) {
+  if (!tuning().trunk_fuse || !g.w || !g.ready || !fused_supported(p, et, nullptr)) return false;
+  if (p.ntaps != 1 || p.dy[0] || p.dx[0] || p.istride != 1 || p.ostride != 1) return false;
+  if (g.in.H != p.MH || g.in.W != p.MW || g.in.C != p.Cin || (g.in.pitch & 1) || (g.in.coff & 1) || (p.in.pitch & 1) || (p.in.coff & 1)) return false;
+  if ((long long)p.N * p.MH * p.MW * (g.in.pitch > p.in.pitch ? g.in.pitch : p.in.pitch) >= (1ll << 31)) return false;   // 32-bit word indices in the math warps
+  if (p.MH % kTH || p.MW % kTW) return false;            // the math warps work on 8 x 16 pixel tiles
+  const int m_tiles = p.N * (p.MH / kTH) * (p.MW / kTW);
+  return want_pair(m_tiles, make_ntiling(p.Cout), 1, num_sms);
+}
+cudaError_t launch_conv_fused_dwg(const ConvParams& p, int et, const DwGlobal& g, int num_sms, cudaStream_t s) {
+  return launch_impl(&p, 1, et, nullptr, &g, num_sms, s);
+}
+
+static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const float* dw, const DwGlobal* g, int num_sms, cudaStream_t s) {
   const ConvParams& p = ps[0];
   FusedArgs a;
   memset(&a, 0, sizeof a);
@@ -651,13 +869,16 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
   }
   a.nt = make_ntiling(p.Cout);
   a.dw_mode = dw ? 1 : 0;
+  a.dw_cols = tuning().dw_cols;
   a.dw_w = dw;
   a.has_res = p.res.ptr ? 1 : 0;
   a.nchunks = (p.Cin + kBK - 1) / kBK;
   a.w_kblocks = p.wtaps * a.nchunks;
-  a.tiles_x = p.MW / kTW;
-  a.tiles_per_img = (p.MH / kTH) * a.tiles_x;
-  a.m_tiles = p.N * a.tiles_per_img;
+  if (!pick_tile(p.MH, p.MW, p.N, &a.bw, &a.bh, &a.bn)) return cudaErrorInvalidValue;
+  a.a_tile_bytes = a.bw * a.bh * a.bn * 128;
+  a.tiles_x = p.MW / a.bw;
+  a.tiles_per_img = ((p.MH + a.bh - 1) / a.bh) * a.tiles_x;
+  a.m_tiles = ((p.N + a.bn - 1) / a.bn) * a.tiles_per_img;
   a.b_stage_bytes = ((a.nt.maxrows * 128) + 1023) & ~1023;
   a.d_nt = make_fastdiv((uint32_t)a.nt.nt); a.d_tpi = make_fastdiv((uint32_t)a.tiles_per_img);
   a.d_tx = make_fastdiv((uint32_t)a.tiles_x); a.d_chunks = make_fastdiv((uint32_t)a.nchunks);
@@ -688,13 +909,16 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
       return cudaErrorInvalidValue;
     }
   } else {
-    // CTA pairs for wide N tiles (the GEMM is bound by operand bytes into the SM): half a B stage per CTA
-    const int items_pair = (a.m_tiles >> 1) * a.nt.nt * nvar;
-    const Tuning& tn = tuning();
-    const int min_items = tn.pair_min_items >= 0 ? tn.pair_min_items : num_sms;   // fewer pair items than SMs: single CTAs fill the GPU better
-    a.pair = (tn.pair && a.nt.maxrows >= tn.pair_min_rows && !(a.m_tiles & 1) && items_pair >= 1 && items_pair >= min_items) ? 1 : 0;
-    for (int i = 0; i < a.nt.nt && a.pair; ++i)
-      if (a.nt.rows[i] & 31) a.pair = 0;                   // N and N/2 stay multiples of 16
+    a.pair = want_pair(a.m_tiles, a.nt, nvar, num_sms) ? 1 : 0;
+    if (g) {
+      if (!a.pair) return cudaErrorInvalidValue;
+      a.dw_w = g->w;
+      a.dwg_in = reinterpret_cast<const char*>(g->in.ptr) + (size_t)g->in.coff * 2;
+      a.dwg_out = reinterpret_cast<char*>(p.in.ptr) + (size_t)p.in.coff * 2;
+      a.dwg_in_pitch = g->in.pitch; a.dwg_out_pitch = p.in.pitch; a.dwg_H = p.MH; a.dwg_W = p.MW;
+      a.dwg_ready = g->ready;
+      a.dwg_target = (kMathThreads / 32) * a.nchunks;      // 16 warps per (M tile, chunk) item
+    }
     if (a.pair) a.b_stage_bytes = (((a.nt.maxrows >> 1) * 128) + 1023) & ~1023;
     a.SA = kMaxStages; a.SH = 0;
     a.SB = a.SA;
@@ -731,8 +955,8 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
     if (!tma_encode_nhwc(&tin, bf16, in_base, p.Cin, p.in.W, p.in.H, p.N, p.in.pitch, kBK, kHaloW, kHaloH, 1, false))
       return cudaErrorInvalidValue;
   } else {
-    if (!tma_encode_nhwc(&tin, bf16, in_base, p.Cin, p.in.W, p.in.H, p.N, p.in.pitch, kBK, kTW * p.istride, kTH * p.istride,
-                         p.istride, true))
+    if (!tma_encode_nhwc(&tin, bf16, in_base, p.Cin, p.in.W, p.in.H, p.N, p.in.pitch, kBK, a.bw * p.istride, a.bh * p.istride,
+                         p.istride, true, a.bn))
       return cudaErrorInvalidValue;
   }
   for (int v = 0; v < nvar; ++v) {  // output view on the virtual grid: pixel (my, mx) -> out pixel (my*ostride + oy0, mx*ostride + ox0)
@@ -740,13 +964,13 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
     const size_t sx = (size_t)q.ostride * q.out.pitch, sy = (size_t)q.ostride * q.out.W * q.out.pitch,
                  sn = (size_t)q.out.H * q.out.W * q.out.pitch;
     void* ob = reinterpret_cast<char*>(q.out.ptr) + (((size_t)q.oy0 * q.out.W + q.ox0) * q.out.pitch + q.out.coff) * 2;
-    if (!tma_encode_view(&tout.m[v], bf16, ob, q.Cout, q.MW, q.MH, q.N, sx, sy, sn, 64, kTW, kTH, true)) return cudaErrorInvalidValue;
+    if (!tma_encode_view(&tout.m[v], bf16, ob, q.Cout, q.MW, q.MH, q.N, sx, sy, sn, 64, a.bw, a.bh, true, a.bn)) return cudaErrorInvalidValue;
   }
   if (a.has_res) {
     const size_t rx = (size_t)p.ostride * p.res.pitch, ry = (size_t)p.ostride * p.res.W * p.res.pitch,
                  rn = (size_t)p.res.H * p.res.W * p.res.pitch;
     void* rb = reinterpret_cast<char*>(p.res.ptr) + (((size_t)p.oy0 * p.res.W + p.ox0) * p.res.pitch + p.res.coff) * 2;
-    if (!tma_encode_view(&tres, bf16, rb, p.Cout, p.MW, p.MH, p.N, rx, ry, rn, 64, kTW, kTH, true)) return cudaErrorInvalidValue;
+    if (!tma_encode_view(&tres, bf16, rb, p.Cout, p.MW, p.MH, p.N, rx, ry, rn, 64, a.bw, a.bh, true, a.bn)) return cudaErrorInvalidValue;
   }
   const size_t smem = fused_smem_bytes(a);
   const int total_tiles = a.m_tiles * a.nt.nt * nvar;
@@ -759,13 +983,15 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
     grid = 2 * ncl;
   } else if (nvar == 4 && grid > 1 && !(grid & 1)) --grid;   // a CTA strides the item list by the grid size: keep it odd so every CTA sees all 4 phases (8/4/4/2 k-blocks)
 #define EMD_DISPATCH(TT)                                                                                                   \
-  (a.dw_mode ? (a.has_res ? launch_t<TT, true, true, false>(a, tin, tout, tres, tw, grid, smem, s)                         \
+  (g ? (a.has_res ? launch_t<TT, false, true, true, true>(a, tin, tout, tres, tw, grid, smem, s)                           \
+                  : launch_t<TT, false, false, true, true>(a, tin, tout, tres, tw, grid, smem, s))                         \
+   : a.dw_mode ? (a.has_res ? launch_t<TT, true, true, false>(a, tin, tout, tres, tw, grid, smem, s)                         \
                           : launch_t<TT, true, false, false>(a, tin, tout, tres, tw, grid, smem, s))                       \
    : a.pair  ? (a.has_res ? launch_t<TT, false, true, true>(a, tin, tout, tres, tw, grid, smem, s)                         \
                           : launch_t<TT, false, false, true>(a, tin, tout, tres, tw, grid, smem, s))                       \
              : (a.has_res ? launch_t<TT, false, true, false>(a, tin, tout, tres, tw, grid, smem, s)                        \
                           : launch_t<TT, false, false, false>(a, tin, tout, tres, tw, grid, smem, s)))
-  last_launch_kind() = a.dw_mode ? LK_FUSED_DW : (a.pair ? LK_FUSED_PAIR : LK_FUSED_TAPS);
+  last_launch_kind() = g ? LK_FUSED_PAIR_DW : a.dw_mode ? LK_FUSED_DW : (a.pair ? LK_FUSED_PAIR : LK_FUSED_TAPS);
   if (bf16) return EMD_DISPATCH(__nv_bfloat16);
   return EMD_DISPATCH(__half);
 #undef EMD_DISPATCH

@@ -27,6 +27,14 @@ template <> __device__ __forceinline__ float from_f<float>(float v) { return v; 
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 
+// two 16-bit values in one 32-bit word <-> two floats
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t u);
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) { __nv_bfloat162 v = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+
 template <typename T, int V> struct VecIO;
 template <> struct VecIO<float, 4> {
   static __device__ __forceinline__ void ld(const float* p, float* v) {
@@ -277,6 +285,112 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const DwParams p) {
   TO* op = reinterpret_cast<TO*>(p.out.ptr) +
            (((size_t)n * p.out.H + oy) * p.out.W + ox) * p.out.pitch + p.out.coff + g * V;
   VecIO<TO, V>::st(op, acc);
+}
+
+// Strip form for the 16-bit modes on maps that do not tile into the 8 x 16 pixel blocks of the TMA-fed kernel (emd_dw.cu) -- the
+// 24^2 / 12^2 / 6^2 maps of 96 x 96 crops (small_scans shape), where the one-thread-per-pixel kernel above re-read the nine
+// weights and the nine inputs of every output (21 % of the HBM peak).  A warp = the 32 channel pairs (64 channels) of one
+// pixel column of one image; it slides the 3x3 window down a block of up to kStripRows rows: every LDG.32 / STG.32 of the warp
+// is one 128-byte line, each input row is loaded once per column (3 loads, kAhead rows in flight) and feeds three output rows,
+// the 9 x 2 weights stay in registers.  Stride 1, any rate (TF SAME: pad = rate).  Same tap order as the other depthwise kernels.
+constexpr int kStripRows = 8;
+template <typename T>
+__global__ void __launch_bounds__(256) dw_strip_kernel(const DwParams p, int nchunks, int row_blocks, long long n_items) {
+  constexpr int kAhead = 3;
+  const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (item >= n_items) return;
+  const int lane = threadIdx.x & 31;
+  long long q = item;
+  const int c = (int)(q % nchunks); q /= nchunks;
+  const int x = (int)(q % p.OW); q /= p.OW;
+  const int rb = (int)(q % row_blocks);
+  const int n = (int)(q / row_blocks);
+  const int cw = c * 32 + lane;                              // channel pair
+  if (2 * cw >= p.in.C) return;
+  const int H = p.in.H, W = p.in.W, r = p.rate;
+  const int y0 = rb * kStripRows;
+  const int rows = min(kStripRows, H - y0);
+  const uint32_t* gin = reinterpret_cast<const uint32_t*>(reinterpret_cast<const T*>(p.in.ptr) + p.in.coff);
+  uint32_t* gout = reinterpret_cast<uint32_t*>(reinterpret_cast<T*>(p.out.ptr) + p.out.coff);
+  const int ipitch = p.in.pitch >> 1, opitch = p.out.pitch >> 1;
+  float2 w[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) w[t] = __ldg(reinterpret_cast<const float2*>(p.w + t * p.in.C + 2 * cw));
+  bool x_ok[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) x_ok[i] = x + (i - 1) * r >= 0 && x + (i - 1) * r < W;
+  const size_t ibase = (size_t)n * H * W, obase = ((size_t)n * p.OH + y0) * p.OW + x;
+  // halo row j (j = 0 .. rows + 1) is image row y0 + (j - 1) * r for rate 1; for rate r the three tap rows of output row i are
+  // y0 + i - r, y0 + i, y0 + i + r: walk output rows and load their three tap rows directly when r > 1
+  if (r == 1) {
+    uint32_t raw[kAhead][3];
+    auto load_row = [&](int j) {
+      const int y = y0 - 1 + j;
+      const bool y_ok = y >= 0 && y < H;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        uint32_t v = 0u;
+        if (y_ok && x_ok[i]) v = __ldg(gin + (ibase + (size_t)y * W + (x + i - 1)) * ipitch + cw);
+        raw[j % kAhead][i] = v;
+      }
+    };
+#pragma unroll
+    for (int j = 0; j < kAhead; ++j) load_row(j);
+    float2 acc[3];
+#pragma unroll
+    for (int j = 0; j < kStripRows + 2; ++j) {
+      if (j >= rows + 2) break;
+      float2 xv[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) xv[i] = unpack2<T>(raw[j % kAhead][i]);
+      if (j + kAhead < kStripRows + 2 && j + kAhead < rows + 2) load_row(j + kAhead);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int o = j - ky;
+        if (o < 0 || o >= kStripRows) continue;
+        float2& d = acc[o % 3];
+        if (ky == 0) d = make_float2(xv[0].x * w[0].x, xv[0].y * w[0].y);
+        else { d.x = fmaf(xv[0].x, w[ky * 3].x, d.x); d.y = fmaf(xv[0].y, w[ky * 3].y, d.y); }
+        d.x = fmaf(xv[1].x, w[ky * 3 + 1].x, d.x); d.y = fmaf(xv[1].y, w[ky * 3 + 1].y, d.y);
+        d.x = fmaf(xv[2].x, w[ky * 3 + 2].x, d.x); d.y = fmaf(xv[2].y, w[ky * 3 + 2].y, d.y);
+      }
+      if (j >= 2 && j - 2 < rows) gout[(obase + (size_t)(j - 2) * p.OW) * opitch + cw] = pack2<T>(acc[(j - 2) % 3].x, acc[(j - 2) % 3].y);
+    }
+  } else {
+    for (int i = 0; i < rows; ++i) {
+      float2 d = make_float2(0.f, 0.f);
+      bool first = true;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int y = y0 + i + (ky - 1) * r;
+        const bool y_ok = y >= 0 && y < H;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          uint32_t v = 0u;
+          if (y_ok && x_ok[kx]) v = __ldg(gin + (ibase + (size_t)y * W + (x + (kx - 1) * r)) * ipitch + cw);
+          const float2 xv = unpack2<T>(v);
+          if (first) { d = make_float2(xv.x * w[0].x, xv.y * w[0].y); first = false; }
+          else { d.x = fmaf(xv.x, w[ky * 3 + kx].x, d.x); d.y = fmaf(xv.y, w[ky * 3 + kx].y, d.y); }
+        }
+      }
+      gout[(obase + (size_t)i * p.OW) * opitch + cw] = pack2<T>(d.x, d.y);
+    }
+  }
+}
+
+bool dw_strip_supported(const DwParams& p, int et) {
+  if (et != ET_BF16 && et != ET_F16) return false;
+  if (p.in_f32 || p.stride != 1 || p.pad != p.rate || p.in.H != p.OH || p.in.W != p.OW) return false;
+  return !((p.in.C | p.in.pitch | p.in.coff | p.out.pitch | p.out.coff) & 1);
+}
+
+cudaError_t launch_dw_strip(const DwParams& p, int et, cudaStream_t s) {
+  const int nchunks = (p.in.C + 63) / 64, row_blocks = (p.OH + kStripRows - 1) / kStripRows;
+  const long long n_items = (long long)p.N * row_blocks * p.OW * nchunks;
+  const unsigned blocks = (unsigned)((n_items * 32 + 255) / 256);
+  if (et == ET_BF16) dw_strip_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(p, nchunks, row_blocks, n_items);
+  else dw_strip_kernel<__half><<<blocks, 256, 0, s>>>(p, nchunks, row_blocks, n_items);
+  return cudaGetLastError();
 }
 
 template <typename TI, typename TO>

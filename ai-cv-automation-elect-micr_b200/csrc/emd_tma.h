@@ -46,12 +46,12 @@ inline EncodeTiledFn tma_encoder() {
 // 4-D map over an NHWC 16-bit activation view: dims (C, W, H, N); box (bc, bw, bh, 1); element strides
 // (1, es, es, 1); zero fill out of range.  base = first channel of the view (16-byte aligned).
 inline bool tma_encode_nhwc(CUtensorMap* map, bool bf16, void* base, int C, int W, int H, int N, int pitch, int bc, int bw,
-                            int bh, int es, bool swizzle128) {
+                            int bh, int es, bool swizzle128, int bn = 1) {
   EncodeTiledFn enc = tma_encoder();
   if (!enc) return false;
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   const cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   const cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
   memset(map, 0, sizeof *map);
   return enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
@@ -62,12 +62,12 @@ inline bool tma_encode_nhwc(CUtensorMap* map, bool bf16, void* base, int C, int 
 // Same, with explicit strides in ELEMENTS between consecutive x, y and n indices (a sub-pixel phase of a
 // transposed convolution's output is the view with sx = 2*pitch, sy = 2*W*pitch).
 inline bool tma_encode_view(CUtensorMap* map, bool bf16, void* base, int C, int W, int H, int N, size_t sx, size_t sy, size_t sn,
-                            int bc, int bw, int bh, bool swizzle128) {
+                            int bc, int bw, int bh, bool swizzle128, int bn = 1) {
   EncodeTiledFn enc = tma_encoder();
   if (!enc) return false;
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   const cuuint64_t strides[3] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)sn * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   memset(map, 0, sizeof *map);
   return enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
@@ -103,15 +103,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // try_wait suspends the thread in hardware until the phase completes or a time limit passes.  With the default (short) limit
+  // the eight epilogue warps of the fused kernel woke ~40 times per tile just to poll again -- 7 % of the issue slots of a kernel
+  // whose depthwise math is issue-bound (ncu, deconv0_0) -- so the limit is stated: 4 us, re-armed until the phase completes.
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity) : "memory");
+      "}" ::"r"(bar), "r"(parity), "r"(4000u) : "memory");
 }
 // non-blocking probe of a phase (true = that phase has completed)
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
@@ -137,6 +140,13 @@ __device__ __forceinline__ bool mbar_try_wait_ns(uint32_t bar, uint32_t parity, 
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// all state spaces: generic-proxy writes to GLOBAL memory (observed through an acquire) before this thread's TMA loads of them
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 // 4-D tiled TMA load (c, x, y, n); out-of-range coordinates are zero-filled = TF SAME padding
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c, int x, int y, int n, uint32_t bar) {
   asm volatile(

@@ -54,6 +54,17 @@ def _resize_bilinear(img, size):
         return (top * (1 - wy) + bot * wy).astype(img.dtype)
 
 
+def preprocess_crop(img, size=CROPSIZE):
+    """``Denoiser.preprocess`` (DEN:632-643) as a function: resize to size x size, scale0to1, NaN/Inf -> 0.5, scale0to1,
+    reshape to (1, size, size, 1).  The order is the class file's (min-max BEFORE the NaN/Inf replacement, App. D-5) -- this
+    is the single-crop path; whole micrographs go through ``denoise``'s repaired normalisation on the GPU."""
+    img = _resize_bilinear(np.asarray(img), size)
+    img = scale0to1(img)
+    img[np.isnan(img)] = 0.5
+    img[np.isinf(img)] = 0.5
+    return scale0to1(img).reshape(1, size, size, 1)
+
+
 class Denoiser(object):
     """Creates denoiser instance (DEN:584-630).
 
@@ -96,12 +107,7 @@ class Denoiser(object):
 
     def preprocess(self, img):
         """DEN:632-643: resize to the crop size, scale0to1, NaN/Inf -> 0.5, scale0to1, reshape."""
-        s = self.cropsize
-        img = _resize_bilinear(np.asarray(img), s)
-        img = scale0to1(img)
-        img[np.isnan(img)] = 0.5
-        img[np.isinf(img)] = 0.5
-        return scale0to1(img).reshape(1, s, s, 1)
+        return preprocess_crop(img, self.cropsize)
 
     def denoise_crop(self, img, preprocess=True, postprocess=True):
         """DEN:645-651: one forward pass.  Returns (S,S) clipped if postprocess, else the raw

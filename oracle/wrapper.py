@@ -37,6 +37,30 @@ def normalise(img):
     return scale0to1(img)
 
 
+def preprocess_crop(img, size=512):
+    """``Denoiser.preprocess`` exactly as the class file has it (DEN:632-643), used by ``denoise_crop(preprocess=True)``:
+    cv2.resize to size x size (INTER_LINEAR: half-pixel centres, edge replicate), scale0to1, NaN -> 0.5, Inf -> 0.5,
+    scale0to1 again, reshape to (1, size, size, 1).  The first min-max runs BEFORE the NaN/Inf replacement (App. D-5): one NaN
+    turns the whole crop into 0.5.  The resize is restated in numpy so the check does not depend on OpenCV."""
+    img = np.asarray(img)
+    h, w = img.shape
+    fy = (np.arange(size, dtype=np.float64) + 0.5) * (h / size) - 0.5     # cv2: src = (dst + 0.5) * scale - 0.5
+    fx = (np.arange(size, dtype=np.float64) + 0.5) * (w / size) - 0.5
+    y0 = np.floor(fy).astype(np.int64); x0 = np.floor(fx).astype(np.int64)
+    wy = (fy - y0).astype(np.float32); wx = (fx - x0).astype(np.float32)
+    y0c, y1c = np.clip(y0, 0, h - 1), np.clip(y0 + 1, 0, h - 1)
+    x0c, x1c = np.clip(x0, 0, w - 1), np.clip(x0 + 1, 0, w - 1)
+    src = img.astype(np.float32)
+    rows = src[:, x0c] * (1.0 - wx)[None, :] + src[:, x1c] * wx[None, :]  # horizontal pass, then vertical (cv2's order)
+    out = rows[y0c] * (1.0 - wy)[:, None] + rows[y1c] * wy[:, None]
+    if (h, w) == (size, size):
+        out = src.copy()            # cv2.resize copies when the size does not change (no 0 * Inf)
+    out = scale0to1(out.astype(img.dtype if np.issubdtype(img.dtype, np.floating) else np.float32))
+    out[np.isnan(out)] = 0.5
+    out[np.isinf(out)] = 0.5
+    return scale0to1(out).reshape(1, size, size, 1)
+
+
 def tile_origins(size: int, crop: int = 512, overlap: int = 80):
     """1-D tile origins: DEN:661-667 with repairs D-2 (int, round-half-even) and D-3 (clamp)."""
     if size < crop:

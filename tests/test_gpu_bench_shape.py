@@ -18,7 +18,8 @@ pytestmark = pytest.mark.gpu
 S = 512
 
 # layer -> (input shape per crop (H, W, C), crops, kernel the bench step uses for it, has residual)
-#   pair = cta_group::2 CTA pairs, taps = single-CTA block-tiled kernel, dw = depthwise computed inside the GEMM kernel
+#   pair = cta_group::2 CTA pairs, taps = single-CTA block-tiled kernel, dw = depthwise computed inside the GEMM kernel's A-operand
+#   producer, pairdw = CTA-pair GEMM whose launch also computes the block's depthwise (math warps, handed over through L2)
 BENCH_LAYERS = {
     # 728-wide trunk at 32x32: three N tiles (256/256/224), pair mode; *_2 add the trunk in the epilogue
     "cnn3": ((64, 64, 256), 16, "pair", False),
@@ -34,7 +35,7 @@ BENCH_LAYERS = {
     "aspp_r6": ((32, 32, 728), 16, "pair", False),
     "aspp_r12": ((32, 32, 728), 16, "pair", False),
     "aspp_r18": ((32, 32, 728), 16, "pair", False),
-    "aspp_pellet": ((32, 32, 3640), 16, "pair", False),
+    "aspp_pellet": ((32, 32, 3640), 16, "taps", False),     # one N tile: 128 pair items at batch 32, fewer than SMs -> single CTAs
     # decoder / encoder at 128x128 .. 512x512
     "residual2_d": ((128, 128, 384), 8, "pair", False),
     "deconv2_0": ((128, 128, 384), 8, "dw", False),
@@ -53,7 +54,7 @@ BENCH_LAYERS = {
     "residual1": ((256, 256, 128), 4, "pair", False),
     "final": ((512, 512, 64), 2, "final", False),
 }
-COUNTER = {"pair": "conv_fused_pair", "taps": "conv_fused_taps", "dw": "conv_fused_dw", "final": "final_tcgen05"}
+COUNTER = {"pair": "conv_fused_pair", "taps": "conv_fused_taps", "dw": "conv_fused_dw", "pairdw": "conv_fused_pair_dw", "final": "final_tcgen05"}
 
 
 @pytest.fixture(scope="module")
@@ -83,7 +84,7 @@ def test_bench_shape_layers_run_the_bench_kernels_and_match_the_oracle(bench_eng
     net = OracleNet(w1, S, dtype=torch.float32)          # FP32 oracle: its own error (~1e-6) is far below the tolerance
     torch.set_num_threads(max(torch.get_num_threads(), 8))
     rng = np.random.default_rng(99)
-    rows, bad = [], []
+    rows, bad, wrong_kernel = [], [], []
     for layer, (shape, n, kind, has_res) in BENCH_LAYERS.items():
         x = (rng.random((n,) + shape, dtype=np.float32) * 4.0).astype(np.float32)       # post-ReLU6-like, O(1), non-negative
         res = None
@@ -97,12 +98,14 @@ def test_bench_shape_layers_run_the_bench_kernels_and_match_the_oracle(bench_eng
         got = eng.run_layer(layer, x, res, mode=mode)
         ran = [k for k, v in COUNTER.items() if eng.counter(v) > before[k]]
         assert eng.counter("conv_cuda_core") == simt0, f"{layer}: CUDA-core fallback in {mode} mode"
-        assert kind in ran, f"{layer}: expected the {kind} kernel at the bench shape, counters moved: {ran}"
+        if kind not in ran:
+            wrong_kernel.append((layer, kind, ran))
         err = rel_l2(got, ref)
         rows.append((layer, n, kind, err))
         if err > TOL_16BIT:
             bad.append((layer, err))
     print("\n".join(f"  {l:14s} n={n:2d} {k:5s} {mode} vs oracle {e:.2e}" for l, n, k, e in rows))
+    assert not wrong_kernel, f"layer, kernel expected at the bench shape, kernels that ran: {wrong_kernel}"
     if mode == "fp16":
         assert not bad, f"fp16 per layer over {TOL_16BIT}: {bad}"
     else:
@@ -117,7 +120,7 @@ def test_pair_kernels_match_single_cta_kernels_bitwise_inputs(bench_engine):
     eng, _ = bench_engine
     rng = np.random.default_rng(5)
     try:
-        for layer, n, has_res in (("mid3_2", 16, True), ("aspp_r12", 16, False), ("aspp_pellet", 16, False), ("deconv1to0", 2, False)):
+        for layer, n, has_res in (("mid5_2", 16, True), ("aspp_r12", 16, False), ("residual2_d", 8, False), ("deconv1to0", 2, False)):
             shape = BENCH_LAYERS[layer][0]
             x = (rng.random((n,) + shape, dtype=np.float32) * 4.0).astype(np.float32)
             res = (rng.random((n, shape[0], shape[1], 728), dtype=np.float32) * 6.0).astype(np.float32) if has_res else None
@@ -138,6 +141,44 @@ def test_pair_kernels_match_single_cta_kernels_bitwise_inputs(bench_engine):
         eng.set_tensor_cores(True)
 
 
+def test_fused_trunk_block_is_bit_identical_to_two_launches(bench_engine):
+    """The 728-wide separable blocks run as ONE launch (depthwise by math warps beside the pair-mode GEMM, result handed over
+    through global memory with per-tile counters).  Same arithmetic in the same order as the two-launch form (depthwise kernel,
+    then GEMM): the outputs must agree bit for bit -- single layers with and without the residual, repeated (the counters are
+    re-zeroed per pass), and a whole 16-crop pass."""
+    eng, _ = bench_engine
+    rng = np.random.default_rng(17)
+    try:
+        eng.set_option("trunk_fuse", 1)
+        for layer, n, has_res in (("mid0_1", 16, False), ("mid5_2", 32, True), ("cnn3_last", 8, False), ("cnn3", 16, False)):
+            shape = BENCH_LAYERS[layer][0]
+            x = (rng.random((n,) + shape, dtype=np.float32) * 4.0).astype(np.float32)
+            res = (rng.random((n, shape[0], shape[1], 728), dtype=np.float32) * 6.0).astype(np.float32) if has_res else None
+            for mode in ("fp16", "bf16"):
+                f0 = eng.counter("conv_fused_pair_dw")
+                a = eng.run_layer(layer, x, res, mode=mode)
+                a2 = eng.run_layer(layer, x, res, mode=mode)
+                assert eng.counter("conv_fused_pair_dw") == f0 + 2
+                eng.set_option("trunk_fuse", 0)
+                b = eng.run_layer(layer, x, res, mode=mode)
+                assert eng.counter("conv_fused_pair_dw") == f0 + 2
+                eng.set_option("trunk_fuse", 1)
+                np.testing.assert_array_equal(a, b, err_msg=f"{layer} {mode}")
+                np.testing.assert_array_equal(a, a2, err_msg=f"{layer} {mode} repeat")
+        crops = rng.random((16, S, S)).astype(np.float32)
+        f0 = eng.counter("conv_fused_pair_dw")
+        a = eng.forward(crops, mode="fp16")
+        assert eng.counter("conv_fused_pair_dw") - f0 >= 38
+        a3 = [eng.forward(crops, mode="fp16") for _ in range(3)][-1]       # graph replay from the third pass on
+        eng.set_option("trunk_fuse", 0)
+        b = eng.forward(crops, mode="fp16")
+        eng.set_option("trunk_fuse", 1)
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(a, a3)
+    finally:
+        eng.set_option("trunk_fuse", 0)
+
+
 def test_forced_pair_mode_on_small_batches(emd):
     """pair_min_items = 1 forces the CTA-pair kernels onto batches that would not reach the threshold, so the small-crop
     suites can cover them too: one 256^2 crop, whole network, pair on vs off."""
@@ -148,9 +189,10 @@ def test_forced_pair_mode_on_small_batches(emd):
     eng.load_weights(emd.weights.pack(make_w1(crops[:, :64, :64], seed=1)))
     try:
         eng.set_option("pair_min_items", 1)
-        p0 = eng.counter("conv_fused_pair")
+        pairs = lambda: eng.counter("conv_fused_pair") + eng.counter("conv_fused_pair_dw")
+        p0 = pairs()
         a = eng.forward(crops, mode="fp16")
-        assert eng.counter("conv_fused_pair") - p0 >= 40          # trunk + ASPP + decoder 1x1s + transposed convs
+        assert pairs() - p0 >= 40          # trunk + ASPP + decoder 1x1s + transposed convs
         eng.set_option("pair", 0)
         b = eng.forward(crops, mode="fp16")
     finally:

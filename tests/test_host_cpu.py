@@ -2,6 +2,7 @@
 include/emd.h declares, the integer tile planner matches the goldens, the weight exporter folds
 BatchNorm correctly -- and nothing silently falls back to the CPU."""
 import ctypes as C
+import importlib
 import json
 import os
 import re
@@ -153,3 +154,29 @@ def test_weight_exporter_covers_both_graph_variants():
     assert f["aspp_r12/dw"].shape == (9, 728) and f["aspp_r12/w"].shape == (728, 728)
     blob = w.pack(w.init_reference_weights(0, "B"), "B")
     assert blob[:8] == b"EMDW0001" and int.from_bytes(blob[12:16], "little") == 1
+
+
+def test_preprocess_crop_values_match_the_reference_order(emd):
+    """Denoiser.preprocess (DEN:632-643), the single-crop path: VALUES against the numpy restatement in oracle/wrapper.py
+    (which spells out cv2.resize's INTER_LINEAR arithmetic) -- up- and down-scaling, float32 and float64, and the class
+    file's order of operations: min-max runs before the NaN/Inf replacement, so one NaN flattens the crop to 0.5 and an Inf
+    ends up as the only 1.0."""
+    from oracle import wrapper as W
+    den = importlib.import_module("ai-cv-automation-elect-micr_b200.denoiser")
+    rng = np.random.default_rng(12)
+    for shape, dtype in (((100, 80), np.float32), ((64, 64), np.float32), ((150, 333), np.float64), ((40, 200), np.float32)):
+        img = (rng.random(shape) * 900 + 50).astype(dtype)
+        got, ref = den.preprocess_crop(img.copy(), 64), W.preprocess_crop(img.copy(), 64)
+        assert got.shape == ref.shape == (1, 64, 64, 1) and got.dtype == np.float32
+        assert np.abs(got - ref).max() <= 2e-6, shape
+        assert got.min() == 0.0 and got.max() == 1.0
+    img = rng.random((64, 64)).astype(np.float32)
+    img[3, 4] = np.nan
+    assert (den.preprocess_crop(img.copy(), 64) == 0.5).all() and (W.preprocess_crop(img.copy(), 64) == 0.5).all()
+    img = rng.random((64, 64)).astype(np.float32)
+    img[10, 20] = np.inf
+    got = den.preprocess_crop(img.copy(), 64)
+    np.testing.assert_array_equal(got, W.preprocess_crop(img.copy(), 64))
+    assert got[0, 10, 20, 0] == 1.0 and (np.delete(got.ravel(), 10 * 64 + 20) == 0.0).all()
+    const = np.full((32, 48), 7.0, np.float32)
+    assert (den.preprocess_crop(const, 64) == 0.5).all()

@@ -16,7 +16,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--crop", type=int, default=512)
-    ap.add_argument("--mode", default="bf16")
+    ap.add_argument("--mode", default="fp16")
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-tc", action="store_true")
     a = ap.parse_args()

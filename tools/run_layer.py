@@ -15,7 +15,7 @@ def main():
     ap.add_argument("--layer", required=True)
     ap.add_argument("--n", type=int, default=4)
     ap.add_argument("--crop", type=int, default=512)
-    ap.add_argument("--mode", default="bf16")
+    ap.add_argument("--mode", default="fp16")
     ap.add_argument("--reps", type=int, default=3)
     a = ap.parse_args()
     import ctypes as C

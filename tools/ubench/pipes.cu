@@ -78,6 +78,33 @@ __global__ void __launch_bounds__(512) k(float* out, long long* cycles, int iter
             asm volatile("mul.lo.u32 %0, %1, 65536;" : "=r"(u[i]) : "r"(u[i + 1]));
           }
         }
+      } else if (OP == 12 || OP == 13) {  // 4 FFMA2 + 4 of {cvt.f32.f16 (HADD2.F32) (12), shift + mask = integer FP16 unpack (13)}
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          unsigned long long x = ((unsigned long long)__float_as_uint(a[i + 1]) << 32) | __float_as_uint(a[i]);
+          unsigned long long w = ((unsigned long long)__float_as_uint(w1) << 32) | __float_as_uint(w0);
+          unsigned long long c = ((unsigned long long)__float_as_uint(b[i + 1]) << 32) | __float_as_uint(b[i]);
+          unsigned long long d;
+          asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(x), "l"(w), "l"(c));
+          a[i] = __uint_as_float((uint32_t)d); a[i + 1] = __uint_as_float((uint32_t)(d >> 32));
+          if (OP == 12) {
+            unsigned short xl, xh;
+            asm("mov.b32 {%0,%1}, %2;" : "=h"(xl), "=h"(xh) : "r"(u[i]));
+            asm volatile("cvt.f32.f16 %0, %1;" : "=f"(b[i]) : "h"(xl));
+          } else {
+            uint32_t t;
+            asm volatile("shr.u32 %0, %1, 3;" : "=r"(t) : "r"(u[i + 1]));
+            asm volatile("and.b32 %0, %1, 0x0FFFE000;" : "=r"(u[i]) : "r"(t));
+          }
+        }
+      } else if (OP == 14) {  // cvt.f32.f16 alone
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          unsigned short xl, xh;
+          asm("mov.b32 {%0,%1}, %2;" : "=h"(xl), "=h"(xh) : "r"(u[i]));
+          asm volatile("cvt.f32.f16 %0, %1;" : "=f"(a[i]) : "h"(i & 1 ? xh : xl));
+          u[i] += __float_as_uint(a[i]);
+        }
       } else if (OP == 6) {  // HFMA2 fp16
 #pragma unroll
         for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(u[i]) : "r"(__float_as_uint(w0)), "r"(__float_as_uint(b[i])));
@@ -118,6 +145,9 @@ int main() {
   run<9>("4FFMA2+4FHFMA", 64);
   run<10>("4FFMA2+4LOP3", 64);
   run<11>("4FFMA2+4IMAD", 64);
+  run<12>("4FFMA2+4CVT.F16", 64);
+  run<13>("4FFMA2+4(SHR,AND)", 96);
+  run<14>("CVT.F32.F16+IADD", 128);
   run<2>("HFMA2.BF16", 64);
   run<6>("HFMA2.F16", 64);
   run<3>("SHL16+XOR", 64);
