@@ -52,7 +52,6 @@ struct Step {
   float ms = 0.f;
   double flops = 0, bytes = 0;  // per crop: algorithmic FLOPs and (16-bit storage) HBM bytes
   double in_bytes = 0;          // the part of `bytes` that is the read of the step's input
-  bool via_l2 = false;          // last run: fused, with the depthwise result handed over through global memory (counted as traffic)
   bool fused = false;           // last run: SK_DW computed inside the next step's GEMM kernel / SK_CONV that absorbed it
   int nlaunch = 0;              // kernels launched for this step in the last run
 };
@@ -110,7 +109,6 @@ struct emd_engine {
     double* d_minmax = nullptr; char* d_partial = nullptr; size_t mm_bytes = 0, partial_bytes = 0;
     cudaEvent_t ev_pre = nullptr, ev_net = nullptr, ev_post = nullptr;
   } slots[2];
-  int* d_flags = nullptr; int flags_stride = 0;          // per-step counters of the fused 728-wide separable blocks (emd_fused.cu, kDwG)
   cudaStream_t s_pre = nullptr, s_post = nullptr;
   cudaEvent_t ev_img_start = nullptr;
   std::vector<cudaEvent_t> events;
@@ -503,7 +501,6 @@ struct ExecCtx {
   float* d_out;       // network output (device, f32)
   std::vector<Override> ov;
   int b0 = 0;         // first crop of the batch this step works on (a slice of the batch: every view starts b0 images in)
-  bool flags_ready = false;   // the per-step counters were zeroed for this pass and no earlier part of it has used this step's slice
 };
 
 View make_view(const ExecCtx& c, Ref r) {
@@ -593,38 +590,11 @@ int step_error(emd_engine* e, int idx, cudaError_t r) {
   return fail(e, EMD_ECUDA, "step %s: %s", e->steps[idx].name.c_str(), cudaGetErrorString(r));
 }
 
-// A stride-1 separable block with several N tiles (728-wide): depthwise by math warps beside the pair-mode GEMM, handed over through
-// global memory inside ONE launch (emd_fused.cu, kDwG).  Needs this pass's zeroed counters and the whole batch in one step.
-bool dwg_fusable(const ExecCtx& c, int conv_idx, ConvParams* out, DwGlobal* gout) {
-  emd_engine* e = c.e;
-  if (c.et == ET_F32 || !e->use_umma || !c.flags_ready || c.b0 != 0 || !e->d_flags || conv_idx < 1 || conv_idx >= (int)e->steps.size()) return false;
-  const Step& s = e->steps[conv_idx];
-  const Step& d = e->steps[conv_idx - 1];
-  if (s.kind != SK_CONV || s.k != 1 || s.stride != 1 || !s.w16[c.et]) return false;
-  if (d.kind != SK_DW || d.layer != s.layer || d.stride != 1 || d.rate != 1 || d.Cin == 1 || e->tensors[d.in.t].external) return false;
-  ConvParams p{};
-  conv_params(c, s, p);
-  DwGlobal g{make_view(c, d.in), d.dw, e->d_flags + (size_t)conv_idx * e->flags_stride};
-  const Tensor& to = e->tensors[s.out.t];
-  if (c.n * (to.H / 8) * (to.W / 16) + 1 > e->flags_stride) return false;
-  if (!fused_dwg_supported(p, c.et, g, e->num_sms)) return false;
-  if (out) *out = p;
-  if (gout) *gout = g;
-  return true;
-}
-
-int zero_flags(emd_engine* e, ExecCtx& c) {
-  if (!e->d_flags) return EMD_OK;
-  CU(e, cudaMemsetAsync(e->d_flags, 0, (size_t)e->steps.size() * e->flags_stride * sizeof(int), c.s));
-  c.flags_ready = true;
-  return EMD_OK;
-}
-
 cudaError_t run_step_impl(ExecCtx& c, int idx);
 cudaError_t run_step(ExecCtx& c, int idx) {
   Step& s = c.e->steps[idx];
   const long long before = c.e->cnt.launches;
-  s.fused = false; s.via_l2 = false;
+  s.fused = false;
   cudaError_t r = run_step_impl(c, idx);
   s.nlaunch = (int)(c.e->cnt.launches - before);
   return r;
@@ -639,7 +609,6 @@ cudaError_t run_step_impl(ExecCtx& c, int idx) {
     case SK_DW: {
       if (s.Cin == 1) { s.fused = true; return cudaSuccess; }  // 1-channel stem: the depthwise is fused into the pointwise kernel below
       if (dw_fusable(c, idx + 1, nullptr)) { s.fused = true; return cudaSuccess; }  // computed inside the pointwise GEMM's producer warps
-      if (dwg_fusable(c, idx + 1, nullptr, nullptr)) { s.fused = true; s.via_l2 = true; return cudaSuccess; }   // computed by the GEMM launch's math warps
       DwParams p{};
       p.in = make_view(c, s.in); p.out = make_view(c, s.out);
       p.N = c.n; p.OH = to.H; p.OW = to.W; p.stride = s.stride; p.rate = s.rate;
@@ -687,14 +656,6 @@ cudaError_t run_step_impl(ExecCtx& c, int idx) {
         e->cnt.umma++;
         e->cnt.kind[LK_FUSED_DW]++;
         return launch_conv_fused(p, c.et, e->steps[idx - 1].dw, e->num_sms, c.s);
-      }
-      DwGlobal g{};
-      if (dwg_fusable(c, idx, &p, &g)) {
-        s.fused = true; s.via_l2 = true;
-        e->cnt.launches++;
-        e->cnt.umma++;
-        e->cnt.kind[LK_FUSED_PAIR_DW]++;
-        return launch_conv_fused_dwg(p, c.et, g, e->num_sms, c.s);
       }
       p = ConvParams{};
       conv_params(c, s, p);
@@ -748,7 +709,6 @@ int run_network_direct(emd_engine* e, const float* d_in, float* d_out, int n, in
     for (auto& ev : e->events) CU(e, cudaEventCreate(&ev));
   }
   e->last_n = n; e->last_et = c.et;
-  { int zrc = zero_flags(e, c); if (zrc) return zrc; }
   for (size_t i = 0; i < e->steps.size(); ++i) {
     if (e->profile) CU(e, cudaEventRecord(e->events[i], s));
     cudaError_t r = run_step(c, (int)i);
@@ -787,13 +747,9 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
   const int nh = halves ? (parts_env == 4 && n >= 32 ? 4 : 2) : 1;
   auto part_lo = [&](int h) { return (int)((long long)n * h / nh); };
   e->last_n = n; e->last_et = c.et;
-  { int zrc = zero_flags(e, c); if (zrc) return zrc; }
   auto step = [&](int i, int b0, int nb) -> int {
     c.b0 = b0; c.n = nb;
-    const bool fr = c.flags_ready;
-    c.flags_ready = fr && b0 == 0 && nb == n;      // a step that runs once per slice would count into the same counters twice
     cudaError_t r = run_step(c, i);
-    c.flags_ready = fr;
     c.b0 = 0; c.n = n;
     return r == cudaSuccess ? EMD_OK : step_error(e, i, r);
   };
@@ -1029,16 +985,6 @@ int emd_create(emd_engine** out, int device, int cropsize, int variant, int max_
   CUC(cudaMalloc(&e->d_minmax, 2 * sizeof(double)));
   CUC(cudaMalloc(&e->d_partial, minmax_partial_bytes()));
   CUC(cudaMalloc(&e->d_origins, 512 * sizeof(int)));
-  for (size_t i = 1; i < e->steps.size(); ++i) {   // counters only for the blocks that can take that route: several N tiles, stride-1 depthwise in front
-    const Step &st = e->steps[i], &dws = e->steps[i - 1];
-    if (st.kind == SK_CONV && st.k == 1 && st.stride == 1 && make_ntiling(st.Cout).nt > 1 && dws.kind == SK_DW && dws.layer == st.layer &&
-        dws.stride == 1 && dws.rate == 1) {
-      const Tensor& to = e->tensors[st.out.t];
-      e->flags_stride = std::max(e->flags_stride, max_batch * (to.H / 8) * (to.W / 16) + 1);
-    }
-  }
-  e->flags_stride = std::max(e->flags_stride, 2);
-  CUC(cudaMalloc(&e->d_flags, e->steps.size() * (size_t)e->flags_stride * sizeof(int)));
 #undef CUC
   *out = e;
   return EMD_OK;
@@ -1051,7 +997,7 @@ int emd_destroy(emd_engine* e) {
   for (void* p : e->w16_allocs) cudaFree(p);
   for (void* p : {(void*)e->arena, (void*)e->d_blob, (void*)e->d_stage_in, (void*)e->d_stage_out, e->d_img_raw, (void*)e->d_q_a, (void*)e->d_q_b, (void*)e->d_q_partial,
                   (void*)e->d_img, (void*)e->d_crops, (void*)e->d_tiles, (void*)e->d_sout, (void*)e->d_minmax,
-                  e->d_partial, (void*)e->d_origins, (void*)e->d_flags})
+                  e->d_partial, (void*)e->d_origins})
     if (p) cudaFree(p);
   for (auto& sl : e->slots) {
     for (void* p : {(void*)sl.d_raw, (void*)sl.d_norm, (void*)sl.d_crops, (void*)sl.d_tiles, (void*)sl.d_sout, (void*)sl.d_minmax, (void*)sl.d_partial})
@@ -1535,7 +1481,6 @@ int emd_run_layer(emd_engine* e, const char* name, const float* in, const float*
   c.ov.push_back(Override{rin.t, d_in});
   c.ov.push_back(Override{rout.t, d_out});
   if (rres.t >= 0) c.ov.push_back(Override{rres.t, d_res});
-  { int zrc = zero_flags(e, c); if (zrc) return zrc; }
   for (int i : idx) {
     cudaError_t r = run_step(c, i);
     if (r != cudaSuccess) return step_error(e, i, r);
@@ -1557,7 +1502,7 @@ long long emd_counter(const emd_engine* e, const char* name) {
   if (!e || !name) return -1;
   static const struct { const char* n; int k; } kinds[] = {
       {"conv_cuda_core", LK_SIMT}, {"conv_tcgen05_gen1", LK_UMMA_GEN1}, {"conv_fused_taps", LK_FUSED_TAPS}, {"conv_fused_pair", LK_FUSED_PAIR},
-      {"conv_fused_dw", LK_FUSED_DW}, {"conv_fused_pair_dw", LK_FUSED_PAIR_DW}, {"final_tcgen05", LK_FINAL_UMMA}, {"final_cuda_core", LK_FINAL_TMA}};
+      {"conv_fused_dw", LK_FUSED_DW}, {"final_tcgen05", LK_FINAL_UMMA}, {"final_cuda_core", LK_FINAL_TMA}};
   const std::string s = name;
   if (s == "launches") return e->cnt.launches;
   if (s == "tensor_core_launches") return e->cnt.umma;
@@ -1613,7 +1558,7 @@ int emd_step_info(const emd_engine* e, int idx, char* name, size_t name_cap, flo
     // one kernel did depthwise + pointwise: it reads the depthwise INPUT once; the intermediate never reaches HBM
     const Step& d = e->steps[idx - 1];
     fl += d.flops;
-    by += s.via_l2 ? d.bytes : d.in_bytes - s.in_bytes;    // handed over through global memory: the intermediate is written and read
+    by += d.in_bytes - s.in_bytes;
   }
   if (flops) *flops = fl;
   if (bytes) *bytes = by;

@@ -70,12 +70,6 @@ struct FusedArgs {
   int b_res;                 // taps mode: every B block of the launch stays in shared memory, loaded once per CTA (block = tap*nchunks + chunk)
   FastDiv d_nt, d_tpi, d_tx, d_chunks;   // by nt.nt, tiles_per_img, tiles_x, nchunks
   const float* dw_w;         // [9][Cin] FP32, tap-major (dw mode)
-  // depthwise through global memory (kDwG: pair-mode GEMM whose A operand is produced during the launch by the math warps)
-  const void* dwg_in;        // depthwise input, first channel of the view
-  void* dwg_out;             // depthwise result = the GEMM's A tensor (p.in), first channel of the view
-  int dwg_in_pitch, dwg_out_pitch, dwg_H, dwg_W;
-  int* dwg_ready;            // [m_tiles] counters, zeroed before the launch; [m_tiles] = fault flag
-  int dwg_target;            // warps per item x chunks
 };
 
 template <typename T> struct Cv;
@@ -170,8 +164,8 @@ __device__ __forceinline__ void epi_half(const uint32_t (&v)[32], const float* _
 
 struct OutMaps { CUtensorMap m[4]; };   // output tensor map per variant
 
-template <typename T, bool kDw, bool kRes, bool kPair, bool kDwG = false>
-__global__ void __launch_bounds__((kDw || kDwG) ? base_threads(true) + kMathThreads : base_threads(false), 1)
+template <typename T, bool kDw, bool kRes, bool kPair>
+__global__ void __launch_bounds__(kDw ? base_threads(true) + kMathThreads : base_threads(false), 1)
 fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ CUtensorMap tmap_in,
                   const __grid_constant__ OutMaps tmaps_out, const __grid_constant__ CUtensorMap tmap_res,
                   const __grid_constant__ CUtensorMap tmap_w) {
@@ -325,20 +319,6 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
         const char* tbase = wbase + (size_t)a.nt.rows_before[ntile] * a.w_kblocks * 128;
         int n_img, y0, x0;
         tile_coords(a, mt, n_img, y0, x0);
-        if constexpr (kDwG) {
-          // the A operand of this M tile is the depthwise result that the math warps (of any CTA) write to global memory during
-          // this launch: wait until all of its (chunk, warp) parts are published, then order the async proxy (TMA) after them
-          if (elect_one()) {
-            const int* flag = a.dwg_ready + mt;
-            int spins = 0;
-            while (ld_acquire_gpu(flag) < a.dwg_target) {
-              __nanosleep(100);
-              if (++spins > (1 << 22)) { atomicExch(a.dwg_ready + a.m_tiles, 1); break; }   // never hang the GPU: flag the fault, read what is there
-            }
-            fence_proxy_async_all();
-          }
-          __syncwarp();
-        }
         {
           const int xb = x0 * p.istride, yb = y0 * p.istride;
           if (a.b_res && tile == first && elect_one()) {   // first tile of this CTA: bring in every weight block, once
@@ -458,13 +438,16 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
       int n_img, y0, x0;
       tile_coords(a, mt, n_img, y0, x0);
       const int acc = tcount & 1;
-      mbar_wait(bar_tfull + 8u * acc, (uint32_t)((tcount >> 1) & 1));
+      // ONE warp polls the accumulator-full mbarrier, the other seven sleep in a hardware barrier: eight polling warps woke ~30
+      // times per tile each, 7 % of the issue slots of a kernel whose depthwise math is issue-bound (ncu, deconv0_0)
+      if (warp == 0) mbar_wait(bar_tfull + 8u * acc, (uint32_t)((tcount >> 1) & 1));
+      named_bar_sync(2, kEpiThreads);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(acc * a.acc_stride);
       const int nslabs = (n + 63) >> 6;
       // this warp converts the 32-column half `my_half` of every 64-column slab; the accumulator read of slab j+1 is in
       // flight while slab j is converted and stored (the epilogue, not the MMA, paces the output-heavy layers)
-      constexpr bool kMath = kDw || kDwG;        // kernels with depthwise math warps run at 72 registers per thread: no room for a second buffer
+      constexpr bool kMath = kDw;                // the kernel with depthwise math warps runs at 72 registers per thread: no room for a second buffer
       constexpr int kVB = kMath ? 1 : 2;
       uint32_t v[kVB][32];
       const int cbase = my_half * 32;
@@ -631,91 +614,6 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
     }
   }
 
-  if constexpr (kDwG) {
-    if (warp >= kBaseThreads / 32) {
-      // ===================== depthwise math warps, result through global memory (L2) =====================
-      // The 728-wide separable blocks have three N tiles; computing the depthwise in the A-operand producer would repeat it per
-      // N tile.  Here the 16 math warps of every CTA compute it ONCE per (M tile, 64-channel chunk) item -- straight from the
-      // previous layer's output in global memory to a global scratch tensor that stays in L2 -- and publish a per-M-tile
-      // counter; the TMA producers of the GEMM (above) wait for the counter of the tile they are about to load.  The GEMM is
-      // bound by the tensor pipe / operand ingress, so the CUDA-core depthwise hides under it: one launch per separable block
-      // instead of two, and no serial depthwise phase.  Items are walked in M-tile order by all CTAs, the GEMM walks the same
-      // order, and the math warps wait for nothing inside the launch: no cycle, no deadlock.
-      // Thread = 2 channels x 1 pixel column x 8 rows; a warp = the 32 channel pairs of one column (every LDG.32 / STG.32 of the
-      // warp is one 128-byte line), all 16 math warps of the CTA work on the same (M tile, chunk) item, so the three columns a
-      // warp reads are shared with its neighbours through L1.  The loads come straight from global memory (L2): what hides their
-      // latency is depth -- kAhead halo rows (3 loads each) in flight per thread -- which the small register footprint of the
-      // one-column mapping pays for (these warps share the SM with the GEMM's epilogue at 72 registers per thread).
-      constexpr int kAhead = 4;
-      const int tm = threadIdx.x - kBaseThreads;               // 0..511
-      const int cp = tm & 31, x0 = tm >> 5;                     // channel pair, pixel column of the tile
-      const int n_items = a.m_tiles * a.nchunks;
-      const int H = a.dwg_H, W = a.dwg_W;
-      const int ipitch = a.dwg_in_pitch >> 1, opitch = a.dwg_out_pitch >> 1;       // in 32-bit words (channel pairs)
-      const uint32_t* gin = reinterpret_cast<const uint32_t*>(a.dwg_in);
-      uint32_t* gout = reinterpret_cast<uint32_t*>(a.dwg_out);
-      int cur_c = -1;
-      float2 w[9];
-      for (int it = (int)blockIdx.x; it < n_items; it += (int)gridDim.x) {
-        const int mt = (int)fdiv((uint32_t)it, a.d_chunks), c = it - mt * a.nchunks;
-        const int cw = c * (kBK / 2) + cp;                            // channel pair of this lane
-        const bool ch_ok = 2 * cw < p.Cin;
-        if (c != cur_c) {
-          cur_c = c;
-#pragma unroll
-          for (int t = 0; t < 9; ++t) w[t] = ch_ok ? __ldg(reinterpret_cast<const float2*>(a.dw_w + t * p.Cin + 2 * cw)) : make_float2(0.f, 0.f);
-        }
-        int n_img, ty, tx;
-        tile_coords(a, mt, n_img, ty, tx);
-        const int xb = tx + x0 - 1;                                   // leftmost halo column
-        const int irow0 = (n_img * H + ty - 1) * W;                   // pixel index of halo row 0, column 0 (guarded by y_ok when outside)
-        const int opix0 = (n_img * H + ty) * W + tx + x0;
-        bool x_ok[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) x_ok[i] = ch_ok && xb + i >= 0 && xb + i < W;
-        uint32_t raw[kAhead][3];
-        auto load_row = [&](int j) {
-          const int y = ty - 1 + j;
-          const bool y_ok = y >= 0 && y < H;
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            uint32_t v = 0u;
-            if (y_ok && x_ok[i]) v = __ldg(gin + (size_t)(unsigned)((irow0 + j * W + xb + i) * ipitch + cw));
-            raw[j % kAhead][i] = v;
-          }
-        };
-#pragma unroll
-        for (int j = 0; j < kAhead; ++j) load_row(j);
-        float2 acc[3];
-#pragma unroll
-        for (int j = 0; j < kTH + 2; ++j) {                           // halo rows ty - 1 + j
-          float2 x[3];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) x[i] = Cv<T>::up(raw[j % kAhead][i]);
-          if (j + kAhead < kTH + 2) load_row(j + kAhead);             // refill the slot just consumed
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-            const int r = j - ky;
-            if (r < 0 || r >= kTH) continue;
-            float2& d = acc[r % 3];
-            d = ky == 0 ? fmul2(x[0], w[0]) : ffma2(x[0], w[ky * 3], d);
-            d = ffma2(x[1], w[ky * 3 + 1], d);
-            d = ffma2(x[2], w[ky * 3 + 2], d);
-          }
-          if (j >= 2 && ch_ok) {
-            const int r = j - 2;
-            gout[(size_t)(unsigned)((opix0 + r * W) * opitch + cw)] = Cv<T>::pack(acc[r % 3].x, acc[r % 3].y);
-          }
-        }
-        __syncwarp();                                               // orders the other lanes' stores before lane 0's release
-        if (lane == 0) {
-          __threadfence();
-          atomicAdd(a.dwg_ready + mt, 1);
-        }
-      }
-    }
-  }
-
   // teardown: everyone done with TMEM, then the allocating warp frees it
   tc_fence_before();
   __syncthreads();
@@ -732,18 +630,18 @@ size_t fused_smem_bytes(const FusedArgs& a) {
          (size_t)a.SH * kHaloBytes + 2 * kMaxC * sizeof(float) + (6 * kMaxStages + 4 + kMaxRing) * 8 + 16;
 }
 
-template <typename T, bool kDw, bool kRes, bool kPair, bool kDwG = false>
+template <typename T, bool kDw, bool kRes, bool kPair>
 cudaError_t launch_t(const FusedArgs& a, const CUtensorMap& tin, const OutMaps& tout, const CUtensorMap& tres, const CUtensorMap& tw,
                      int grid, size_t smem, cudaStream_t s) {
   static thread_local int attr_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (attr_dev != dev) {
-    cudaError_t r = cudaFuncSetAttribute(fused_conv_kernel<T, kDw, kRes, kPair, kDwG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaError_t r = cudaFuncSetAttribute(fused_conv_kernel<T, kDw, kRes, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (r != cudaSuccess) return r;
     attr_dev = dev;
   }
-  const int block = (kDw || kDwG) ? base_threads(true) + kMathThreads : base_threads(false);
+  const int block = kDw ? base_threads(true) + kMathThreads : base_threads(false);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)block);
@@ -762,7 +660,7 @@ cudaError_t launch_t(const FusedArgs& a, const CUtensorMap& tin, const OutMaps& 
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, fused_conv_kernel<T, kDw, kRes, kPair, kDwG>, a, tin, tout, tres, tw);
+  return cudaLaunchKernelEx(&cfg, fused_conv_kernel<T, kDw, kRes, kPair>, a, tin, tout, tres, tw);
 }
 
 }  // namespace
@@ -821,13 +719,13 @@ bool fused_multi_supported(const ConvParams* ps, int nvar, int et) {
   return true;
 }
 
-static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const float* dw, const DwGlobal* g, int num_sms, cudaStream_t s);
+static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const float* dw, int num_sms, cudaStream_t s);
 
 cudaError_t launch_conv_fused(const ConvParams& p, int et, const float* dw, int num_sms, cudaStream_t s) {
-  return launch_impl(&p, 1, et, dw, nullptr, num_sms, s);
+  return launch_impl(&p, 1, et, dw, num_sms, s);
 }
 cudaError_t launch_conv_fused_multi(const ConvParams* ps, int nvar, int et, int num_sms, cudaStream_t s) {
-  return launch_impl(ps, nvar, et, nullptr, nullptr, num_sms, s);
+  return launch_impl(ps, nvar, et, nullptr, num_sms, s);
 }
 
 // CTA pairs (cta_group::2) for wide N tiles -- the GEMM is bound by operand bytes into the SM, and a pair holds half a B stage
@@ -842,22 +740,7 @@ static bool want_pair(int m_tiles, const NTiling& nt, int nvar, int num_sms) {
   return true;
 }
 
-// A stride-1 separable block with SEVERAL N tiles (the 728-wide trunk): the depthwise is computed once per M tile by math warps
-// that run beside the pair-mode GEMM and hand their result over through global memory (kDwG in the kernel)
-bool fused_dwg_supported(const ConvParams& p, int et, const DwGlobal& g, int num_sms) {
-  if (!tuning().trunk_fuse || !g.w || !g.ready || !fused_supported(p, et, nullptr)) return false;
-  if (p.ntaps != 1 || p.dy[0] || p.dx[0] || p.istride != 1 || p.ostride != 1) return false;
-  if (g.in.H != p.MH || g.in.W != p.MW || g.in.C != p.Cin || (g.in.pitch & 1) || (g.in.coff & 1) || (p.in.pitch & 1) || (p.in.coff & 1)) return false;
-  if ((long long)p.N * p.MH * p.MW * (g.in.pitch > p.in.pitch ? g.in.pitch : p.in.pitch) >= (1ll << 31)) return false;   // 32-bit word indices in the math warps
-  if (p.MH % kTH || p.MW % kTW) return false;            // the math warps work on 8 x 16 pixel tiles
-  const int m_tiles = p.N * (p.MH / kTH) * (p.MW / kTW);
-  return want_pair(m_tiles, make_ntiling(p.Cout), 1, num_sms);
-}
-cudaError_t launch_conv_fused_dwg(const ConvParams& p, int et, const DwGlobal& g, int num_sms, cudaStream_t s) {
-  return launch_impl(&p, 1, et, nullptr, &g, num_sms, s);
-}
-
-static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const float* dw, const DwGlobal* g, int num_sms, cudaStream_t s) {
+static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const float* dw, int num_sms, cudaStream_t s) {
   const ConvParams& p = ps[0];
   FusedArgs a;
   memset(&a, 0, sizeof a);
@@ -910,15 +793,6 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
     }
   } else {
     a.pair = want_pair(a.m_tiles, a.nt, nvar, num_sms) ? 1 : 0;
-    if (g) {
-      if (!a.pair) return cudaErrorInvalidValue;
-      a.dw_w = g->w;
-      a.dwg_in = reinterpret_cast<const char*>(g->in.ptr) + (size_t)g->in.coff * 2;
-      a.dwg_out = reinterpret_cast<char*>(p.in.ptr) + (size_t)p.in.coff * 2;
-      a.dwg_in_pitch = g->in.pitch; a.dwg_out_pitch = p.in.pitch; a.dwg_H = p.MH; a.dwg_W = p.MW;
-      a.dwg_ready = g->ready;
-      a.dwg_target = (kMathThreads / 32) * a.nchunks;      // 16 warps per (M tile, chunk) item
-    }
     if (a.pair) a.b_stage_bytes = (((a.nt.maxrows >> 1) * 128) + 1023) & ~1023;
     a.SA = kMaxStages; a.SH = 0;
     a.SB = a.SA;
@@ -983,15 +857,13 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
     grid = 2 * ncl;
   } else if (nvar == 4 && grid > 1 && !(grid & 1)) --grid;   // a CTA strides the item list by the grid size: keep it odd so every CTA sees all 4 phases (8/4/4/2 k-blocks)
 #define EMD_DISPATCH(TT)                                                                                                   \
-  (g ? (a.has_res ? launch_t<TT, false, true, true, true>(a, tin, tout, tres, tw, grid, smem, s)                           \
-                  : launch_t<TT, false, false, true, true>(a, tin, tout, tres, tw, grid, smem, s))                         \
-   : a.dw_mode ? (a.has_res ? launch_t<TT, true, true, false>(a, tin, tout, tres, tw, grid, smem, s)                         \
+  (a.dw_mode ? (a.has_res ? launch_t<TT, true, true, false>(a, tin, tout, tres, tw, grid, smem, s)                         \
                           : launch_t<TT, true, false, false>(a, tin, tout, tres, tw, grid, smem, s))                       \
    : a.pair  ? (a.has_res ? launch_t<TT, false, true, true>(a, tin, tout, tres, tw, grid, smem, s)                         \
                           : launch_t<TT, false, false, true>(a, tin, tout, tres, tw, grid, smem, s))                       \
              : (a.has_res ? launch_t<TT, false, true, false>(a, tin, tout, tres, tw, grid, smem, s)                        \
                           : launch_t<TT, false, false, false>(a, tin, tout, tres, tw, grid, smem, s)))
-  last_launch_kind() = g ? LK_FUSED_PAIR_DW : a.dw_mode ? LK_FUSED_DW : (a.pair ? LK_FUSED_PAIR : LK_FUSED_TAPS);
+  last_launch_kind() = a.dw_mode ? LK_FUSED_DW : (a.pair ? LK_FUSED_PAIR : LK_FUSED_TAPS);
   if (bf16) return EMD_DISPATCH(__nv_bfloat16);
   return EMD_DISPATCH(__half);
 #undef EMD_DISPATCH

@@ -129,12 +129,6 @@ size_t umma_pack_weights(const float* w, int ntaps, int Cin, int Cout, int et, v
 // depthwise-3x3 producer: dw = [9][Cin] FP32 weights, p.in = the depthwise input)
 bool fused_supported(const ConvParams& p, int et, const float* dw);
 cudaError_t launch_conv_fused(const ConvParams& p, int et, const float* dw, int num_sms, cudaStream_t s);
-// separable block with several N tiles (728-wide trunk): pair-mode GEMM over p.in = the depthwise RESULT tensor, which the same
-// launch's math warps compute from g.in (depthwise input) with weights g.w [9][Cin] and publish through g.ready
-// ([m_tiles + 1] ints, zeroed before the launch; the last one is a fault flag)
-struct DwGlobal { View in; const float* w; int* ready; };
-bool fused_dwg_supported(const ConvParams& p, int et, const DwGlobal& g, int num_sms);
-cudaError_t launch_conv_fused_dwg(const ConvParams& p, int et, const DwGlobal& g, int num_sms, cudaStream_t s);
 // the 4 sub-pixel phases of one transposed conv (same input, weights, epilogue; different taps / output offsets) as ONE launch
 bool fused_multi_supported(const ConvParams* ps, int nvar, int et);
 cudaError_t launch_conv_fused_multi(const ConvParams* ps, int nvar, int et, int num_sms, cudaStream_t s);
@@ -153,7 +147,6 @@ struct Tuning {
   int sliced_io = 1;       // EMD_DISABLE_SLICED_IO: host-buffer passes as the two-chunk pipeline
   int halves = 1;          // EMD_DISABLE_HALVES: no half-batch head / tail in host-buffer passes
   int mid_graph = 1;       // EMD_DISABLE_MID_GRAPH: no graph replay of the whole-batch middle section
-  int trunk_fuse = 0;      // EMD_TRUNK_FUSE=1: the 728-wide separable blocks as ONE launch (depthwise by math warps beside the pair-mode GEMM)
   int dw_strip = 1;        // EMD_DISABLE_DW_STRIP: small-map depthwise on the one-thread-per-pixel kernel
   int dw_cols = 1;         // EMD_DISABLE_DW_COLS: depthwise producer with one pixel column per thread (first form)
   int strict = 0;          // EMD_STRICT=1: a GEMM-class layer of a 16-bit mode that would run on the CUDA-core kernel is an error
@@ -169,7 +162,7 @@ bool tuning_get(const char* name, long long* value);
 inline bool pdl_enabled() { return tuning().pdl != 0; }
 
 // which kernel a conv launcher picked (read by the engine right after the call; per host thread)
-enum LaunchKind { LK_NONE = 0, LK_SIMT, LK_UMMA_GEN1, LK_FUSED_TAPS, LK_FUSED_PAIR, LK_FUSED_DW, LK_FUSED_PAIR_DW, LK_FINAL_UMMA, LK_FINAL_TMA, LK_COUNT };
+enum LaunchKind { LK_NONE = 0, LK_SIMT, LK_UMMA_GEN1, LK_FUSED_TAPS, LK_FUSED_PAIR, LK_FUSED_DW, LK_FINAL_UMMA, LK_FINAL_TMA, LK_COUNT };
 int& last_launch_kind();
 
 // emd_quality.cu: MSE / Huberised loss / SSIM of image pairs (d_out = 3 doubles per pair, d_partial = quality_partial_bytes)

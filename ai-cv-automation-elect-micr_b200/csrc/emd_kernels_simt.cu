@@ -323,16 +323,22 @@ __global__ void __launch_bounds__(256) dw_strip_kernel(const DwParams p, int nch
   // halo row j (j = 0 .. rows + 1) is image row y0 + (j - 1) * r for rate 1; for rate r the three tap rows of output row i are
   // y0 + i - r, y0 + i, y0 + i + r: walk output rows and load their three tap rows directly when r > 1
   if (r == 1) {
+    // running pointers (three input columns, one output column) advanced by one image row per step: the per-load 64-bit index
+    // arithmetic of the first version cost ~20 instructions per load and made the kernel issue-bound (ncu: 1059 instructions per
+    // warp for 30 loads and 72 FMAs)
+    const size_t irs = (size_t)W * ipitch, ors = (size_t)p.OW * opitch;
+    const uint32_t* pin = gin + ((ibase + (size_t)y0 * W + x) * ipitch + cw);      // (y0, x); rows / columns outside the image are never dereferenced
+    pin -= irs;                                                                   // halo row 0 = image row y0 - 1
+    uint32_t* pout = gout + (obase * opitch + cw);
     uint32_t raw[kAhead][3];
-    auto load_row = [&](int j) {
-      const int y = y0 - 1 + j;
-      const bool y_ok = y >= 0 && y < H;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        uint32_t v = 0u;
-        if (y_ok && x_ok[i]) v = __ldg(gin + (ibase + (size_t)y * W + (x + i - 1)) * ipitch + cw);
-        raw[j % kAhead][i] = v;
-      }
+    int yl = y0 - 1;                                                               // image row of the next row to load
+    auto load_row = [&](int slot) {
+      const bool y_ok = yl >= 0 && yl < H;
+      raw[slot][0] = (y_ok && x_ok[0]) ? __ldg(pin - ipitch) : 0u;
+      raw[slot][1] = y_ok ? __ldg(pin) : 0u;
+      raw[slot][2] = (y_ok && x_ok[2]) ? __ldg(pin + ipitch) : 0u;
+      pin += irs;
+      ++yl;
     };
 #pragma unroll
     for (int j = 0; j < kAhead; ++j) load_row(j);
@@ -343,7 +349,7 @@ __global__ void __launch_bounds__(256) dw_strip_kernel(const DwParams p, int nch
       float2 xv[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) xv[i] = unpack2<T>(raw[j % kAhead][i]);
-      if (j + kAhead < kStripRows + 2 && j + kAhead < rows + 2) load_row(j + kAhead);
+      if (j + kAhead < kStripRows + 2 && j + kAhead < rows + 2) load_row(j % kAhead);
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int o = j - ky;
@@ -354,7 +360,10 @@ __global__ void __launch_bounds__(256) dw_strip_kernel(const DwParams p, int nch
         d.x = fmaf(xv[1].x, w[ky * 3 + 1].x, d.x); d.y = fmaf(xv[1].y, w[ky * 3 + 1].y, d.y);
         d.x = fmaf(xv[2].x, w[ky * 3 + 2].x, d.x); d.y = fmaf(xv[2].y, w[ky * 3 + 2].y, d.y);
       }
-      if (j >= 2 && j - 2 < rows) gout[(obase + (size_t)(j - 2) * p.OW) * opitch + cw] = pack2<T>(acc[(j - 2) % 3].x, acc[(j - 2) % 3].y);
+      if (j >= 2 && j - 2 < rows) {
+        *pout = pack2<T>(acc[(j - 2) % 3].x, acc[(j - 2) % 3].y);
+        pout += ors;
+      }
     }
   } else {
     for (int i = 0; i < rows; ++i) {

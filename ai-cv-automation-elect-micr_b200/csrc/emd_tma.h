@@ -103,18 +103,17 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  // try_wait suspends the thread in hardware until the phase completes or a time limit passes.  With the default (short) limit
-  // the eight epilogue warps of the fused kernel woke ~40 times per tile just to poll again -- 7 % of the issue slots of a kernel
-  // whose depthwise math is issue-bound (ncu, deconv0_0) -- so the limit is stated: 4 us, re-armed until the phase completes.
+  // (a stated suspend-time limit -- try_wait's 4th operand -- was measured: ptxas turns it into a PHASECHK + NANOSLEEP loop that
+  // polls as often and executes more instructions; the plain form stays)
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity), "r"(4000u) : "memory");
+      "}" ::"r"(bar), "r"(parity) : "memory");
 }
 // non-blocking probe of a phase (true = that phase has completed)
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
@@ -140,13 +139,6 @@ __device__ __forceinline__ bool mbar_try_wait_ns(uint32_t bar, uint32_t parity, 
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// all state spaces: generic-proxy writes to GLOBAL memory (observed through an acquire) before this thread's TMA loads of them
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 // 4-D tiled TMA load (c, x, y, n); out-of-range coordinates are zero-filled = TF SAME padding
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c, int x, int y, int n, uint32_t bar) {
   asm volatile(

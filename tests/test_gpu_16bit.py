@@ -117,6 +117,31 @@ def test_network_bf16_end_to_end_contract(setup):
     assert rel_l2(eng.forward(setup["crops"], mode="bf16"), ref) <= TOL_16BIT
 
 
+def test_first_generation_kernel_and_small_map_tiles(setup):
+    """Maps that do not tile into 8 x 16 pixel blocks (the 8x8 and 4x4 maps of 64x64 crops) run on the block-tiled kernel with
+    whole-row, multi-image M tiles; the first-generation tcgen05 kernel (cp.async im2col gather) is what remains behind
+    set_option('fused', 0).  Both against the oracle per layer, and against each other."""
+    eng, emd = setup["eng"], setup["emd"]
+    eng.load_weights(emd.weights.pack(setup["w1"]))
+    _, acts = oracle_acts(setup["w1"], setup["crops"])
+    table = layer_io_table()
+    try:
+        for layer in ("cnn3", "cnn3_last", "cnn3_strided", "residual3", "mid4_0", "mid4_2", "aspp_r6", "aspp_pellet", "deconv2to1", "residual2_d"):
+            i, r, o = table[layer]
+            res = None if r is None else acts[r]
+            t0, g0 = eng.counter("conv_fused_taps") + eng.counter("conv_fused_pair"), eng.counter("conv_tcgen05_gen1")
+            a = eng.run_layer(layer, acts[i], res, mode="fp16")
+            assert eng.counter("conv_fused_taps") + eng.counter("conv_fused_pair") > t0 and eng.counter("conv_tcgen05_gen1") == g0, layer
+            eng.set_option("fused", 0)
+            b = eng.run_layer(layer, acts[i], res, mode="fp16")
+            assert eng.counter("conv_tcgen05_gen1") > g0, layer
+            eng.set_option("fused", 1)
+            assert rel_l2(a, acts[o]) <= TOL_16BIT and rel_l2(b, acts[o]) <= TOL_16BIT, (layer, rel_l2(a, acts[o]), rel_l2(b, acts[o]))
+            assert rel_l2(a, b) <= 2e-4, (layer, rel_l2(a, b))
+    finally:
+        eng.set_option("fused", 1)
+
+
 def test_tensor_core_shapes_s96_and_ragged_batch(setup):
     """96x96 crops (small_scans shape): 6x6 maps at stride 16, M tiles that straddle images, dilated
     taps that never land inside the map; batch 3 leaves ragged last tiles."""

@@ -18,8 +18,7 @@ pytestmark = pytest.mark.gpu
 S = 512
 
 # layer -> (input shape per crop (H, W, C), crops, kernel the bench step uses for it, has residual)
-#   pair = cta_group::2 CTA pairs, taps = single-CTA block-tiled kernel, dw = depthwise computed inside the GEMM kernel's A-operand
-#   producer, pairdw = CTA-pair GEMM whose launch also computes the block's depthwise (math warps, handed over through L2)
+#   pair = cta_group::2 CTA pairs, taps = single-CTA block-tiled kernel, dw = depthwise computed inside the GEMM kernel's A-operand producer
 BENCH_LAYERS = {
     # 728-wide trunk at 32x32: three N tiles (256/256/224), pair mode; *_2 add the trunk in the epilogue
     "cnn3": ((64, 64, 256), 16, "pair", False),
@@ -54,7 +53,7 @@ BENCH_LAYERS = {
     "residual1": ((256, 256, 128), 4, "pair", False),
     "final": ((512, 512, 64), 2, "final", False),
 }
-COUNTER = {"pair": "conv_fused_pair", "taps": "conv_fused_taps", "dw": "conv_fused_dw", "pairdw": "conv_fused_pair_dw", "final": "final_tcgen05"}
+COUNTER = {"pair": "conv_fused_pair", "taps": "conv_fused_taps", "dw": "conv_fused_dw", "final": "final_tcgen05"}
 
 
 @pytest.fixture(scope="module")
@@ -141,44 +140,6 @@ def test_pair_kernels_match_single_cta_kernels_bitwise_inputs(bench_engine):
         eng.set_tensor_cores(True)
 
 
-def test_fused_trunk_block_is_bit_identical_to_two_launches(bench_engine):
-    """The 728-wide separable blocks run as ONE launch (depthwise by math warps beside the pair-mode GEMM, result handed over
-    through global memory with per-tile counters).  Same arithmetic in the same order as the two-launch form (depthwise kernel,
-    then GEMM): the outputs must agree bit for bit -- single layers with and without the residual, repeated (the counters are
-    re-zeroed per pass), and a whole 16-crop pass."""
-    eng, _ = bench_engine
-    rng = np.random.default_rng(17)
-    try:
-        eng.set_option("trunk_fuse", 1)
-        for layer, n, has_res in (("mid0_1", 16, False), ("mid5_2", 32, True), ("cnn3_last", 8, False), ("cnn3", 16, False)):
-            shape = BENCH_LAYERS[layer][0]
-            x = (rng.random((n,) + shape, dtype=np.float32) * 4.0).astype(np.float32)
-            res = (rng.random((n, shape[0], shape[1], 728), dtype=np.float32) * 6.0).astype(np.float32) if has_res else None
-            for mode in ("fp16", "bf16"):
-                f0 = eng.counter("conv_fused_pair_dw")
-                a = eng.run_layer(layer, x, res, mode=mode)
-                a2 = eng.run_layer(layer, x, res, mode=mode)
-                assert eng.counter("conv_fused_pair_dw") == f0 + 2
-                eng.set_option("trunk_fuse", 0)
-                b = eng.run_layer(layer, x, res, mode=mode)
-                assert eng.counter("conv_fused_pair_dw") == f0 + 2
-                eng.set_option("trunk_fuse", 1)
-                np.testing.assert_array_equal(a, b, err_msg=f"{layer} {mode}")
-                np.testing.assert_array_equal(a, a2, err_msg=f"{layer} {mode} repeat")
-        crops = rng.random((16, S, S)).astype(np.float32)
-        f0 = eng.counter("conv_fused_pair_dw")
-        a = eng.forward(crops, mode="fp16")
-        assert eng.counter("conv_fused_pair_dw") - f0 >= 38
-        a3 = [eng.forward(crops, mode="fp16") for _ in range(3)][-1]       # graph replay from the third pass on
-        eng.set_option("trunk_fuse", 0)
-        b = eng.forward(crops, mode="fp16")
-        eng.set_option("trunk_fuse", 1)
-        np.testing.assert_array_equal(a, b)
-        np.testing.assert_array_equal(a, a3)
-    finally:
-        eng.set_option("trunk_fuse", 0)
-
-
 def test_forced_pair_mode_on_small_batches(emd):
     """pair_min_items = 1 forces the CTA-pair kernels onto batches that would not reach the threshold, so the small-crop
     suites can cover them too: one 256^2 crop, whole network, pair on vs off."""
@@ -189,10 +150,9 @@ def test_forced_pair_mode_on_small_batches(emd):
     eng.load_weights(emd.weights.pack(make_w1(crops[:, :64, :64], seed=1)))
     try:
         eng.set_option("pair_min_items", 1)
-        pairs = lambda: eng.counter("conv_fused_pair") + eng.counter("conv_fused_pair_dw")
-        p0 = pairs()
+        p0 = eng.counter("conv_fused_pair")
         a = eng.forward(crops, mode="fp16")
-        assert pairs() - p0 >= 40          # trunk + ASPP + decoder 1x1s + transposed convs
+        assert eng.counter("conv_fused_pair") - p0 >= 40          # trunk + ASPP + decoder 1x1s + transposed convs
         eng.set_option("pair", 0)
         b = eng.forward(crops, mode="fp16")
     finally:
