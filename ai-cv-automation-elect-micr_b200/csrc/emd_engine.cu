@@ -617,6 +617,7 @@ cudaError_t run_step_impl(ExecCtx& c, int idx) {
       e->cnt.launches++;
       if (e->use_umma && dw_tma_supported(p, c.et)) return launch_dw_tma(p, c.et, e->num_sms, c.s);
       if (e->use_umma && dw_s2_tma_supported(p, c.et)) return launch_dw_s2_tma(p, c.et, e->num_sms, c.s);
+      if (tuning().dw_tile && dw_tile_supported(p, c.et)) return launch_dw_tile(p, c.et, c.s);
       if (tuning().dw_strip && dw_strip_supported(p, c.et)) return launch_dw_strip(p, c.et, c.s);
       return launch_dw3x3(p, c.et, c.s);
     }

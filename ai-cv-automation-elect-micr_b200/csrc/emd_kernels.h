@@ -80,6 +80,8 @@ cudaError_t launch_conv_simt(const ConvParams& p, int et, cudaStream_t s);
 cudaError_t launch_dw3x3(const DwParams& p, int et, cudaStream_t s);
 bool dw_strip_supported(const DwParams& p, int et);   // 16-bit, stride 1: warp = 64 channels of one pixel column, window slides down the column
 cudaError_t launch_dw_strip(const DwParams& p, int et, cudaStream_t s);
+bool dw_tile_supported(const DwParams& p, int et);    // 16-bit, stride 1, rate 1: warp = 8 x 8 pixel tile x 64 channels, halo staged in smem by cp.async
+cudaError_t launch_dw_tile(const DwParams& p, int et, cudaStream_t s);
 cudaError_t launch_resize(const ResizeParams& p, int et, cudaStream_t s);
 cudaError_t launch_avgpool(const PoolParams& p, int et, cudaStream_t s);
 cudaError_t launch_stem(const StemParams& p, int et, cudaStream_t s);
@@ -147,7 +149,8 @@ struct Tuning {
   int sliced_io = 1;       // EMD_DISABLE_SLICED_IO: host-buffer passes as the two-chunk pipeline
   int halves = 1;          // EMD_DISABLE_HALVES: no half-batch head / tail in host-buffer passes
   int mid_graph = 1;       // EMD_DISABLE_MID_GRAPH: no graph replay of the whole-batch middle section
-  int dw_strip = 1;        // EMD_DISABLE_DW_STRIP: small-map depthwise on the one-thread-per-pixel kernel
+  int dw_tile = 1;         // EMD_DISABLE_DW_TILE: small-map depthwise on the strip kernel (no shared-memory staging)
+  int dw_strip = 1;        // EMD_DISABLE_DW_STRIP: small-map / dilated depthwise on the one-thread-per-pixel kernel
   int dw_cols = 1;         // EMD_DISABLE_DW_COLS: depthwise producer with one pixel column per thread (first form)
   int strict = 0;          // EMD_STRICT=1: a GEMM-class layer of a 16-bit mode that would run on the CUDA-core kernel is an error
   int graph_max_n = 32;    // EMD_GRAPH_MAX_N: largest batch replayed from a graph

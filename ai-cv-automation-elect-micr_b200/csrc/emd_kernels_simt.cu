@@ -402,6 +402,107 @@ cudaError_t launch_dw_strip(const DwParams& p, int et, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+// Small maps (24^2 / 12^2 / 6^2 at 96 x 96 crops), stride 1, rate 1: a warp takes an (up to) 8 x 8 pixel tile of one image and one
+// 64-channel chunk, brings its 10 x 10 pixel halo into shared memory with 4-byte cp.async (lane = channel pair: one 128-byte line
+// per instruction, ~100 loads in flight per warp and no registers held -- the strip kernel's nine loads in flight per warp left
+// it latency-bound at 0.3 of the HBM roofline, and re-read every column three times), then slides the 3x3 window over it in
+// passes of four columns (the thread mapping of the fused kernel's depthwise producer).  Same tap order as the other kernels.
+constexpr int kTileT = 8, kTileHalo = kTileT + 2, kTileWarpBytes = kTileHalo * kTileHalo * 128;
+template <typename T>
+__global__ void __launch_bounds__(256) dw_tile_kernel(const DwParams p, int nchunks, int tiles_x, int tiles_y, long long n_items) {
+  extern __shared__ __align__(16) uint8_t tile_smem[];
+  const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (item >= n_items) return;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  long long q = item;
+  const int c = (int)(q % nchunks); q /= nchunks;
+  const int tx = (int)(q % tiles_x); q /= tiles_x;
+  const int ty = (int)(q % tiles_y);
+  const int n = (int)(q / tiles_y);
+  const int cw = c * 32 + lane;
+  const bool ch_ok = 2 * cw < p.in.C;
+  const int H = p.in.H, W = p.in.W;
+  const int x0 = tx * kTileT, y0 = ty * kTileT;
+  const int tw = min(kTileT, W - x0), th = min(kTileT, H - y0);
+  const uint32_t* gin = reinterpret_cast<const uint32_t*>(reinterpret_cast<const T*>(p.in.ptr) + p.in.coff);
+  uint32_t* gout = reinterpret_cast<uint32_t*>(reinterpret_cast<T*>(p.out.ptr) + p.out.coff);
+  const int ipitch = p.in.pitch >> 1, opitch = p.out.pitch >> 1;
+  uint32_t* sm = reinterpret_cast<uint32_t*>(tile_smem + (size_t)wib * kTileWarpBytes) + lane;      // [halo pixel][32 lanes]
+  const uint32_t sm_addr = (uint32_t)__cvta_generic_to_shared(sm);
+  // halo in: one cp.async per in-bounds halo pixel, zeros elsewhere (TF SAME padding)
+  const uint32_t* img = gin + ((size_t)n * H * W) * ipitch + cw;
+  for (int hy = 0; hy < th + 2; ++hy) {
+    const int y = y0 - 1 + hy;
+    const bool y_ok = y >= 0 && y < H;
+    for (int hx = 0; hx < tw + 2; ++hx) {
+      const int x = x0 - 1 + hx;
+      const int slot = hy * kTileHalo + hx;
+      if (ch_ok && y_ok && x >= 0 && x < W)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sm_addr + (uint32_t)slot * 128u), "l"(img + ((size_t)y * W + x) * ipitch) : "memory");
+      else
+        sm[slot * 32] = 0u;
+    }
+  }
+  float2 w[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) w[t] = ch_ok ? __ldg(reinterpret_cast<const float2*>(p.w + t * p.in.C + 2 * cw)) : make_float2(0.f, 0.f);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+  if (!ch_ok) return;
+  uint32_t* orow0 = gout + (((size_t)n * p.OH + y0) * p.OW + x0) * opitch + cw;
+  for (int cx = 0; cx < tw; cx += 4) {              // passes of four columns
+    const int ncol = min(4, tw - cx);
+    float2 acc[3][4];
+#pragma unroll
+    for (int j = 0; j < kTileHalo; ++j) {           // halo rows y0 - 1 + j
+      if (j >= th + 2) break;
+      float2 x[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) x[i] = (i < ncol + 2) ? unpack2<T>(sm[(j * kTileHalo + cx + i) * 32]) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int r = j - ky;
+        if (r < 0 || r >= kTileT) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float2& d = acc[r % 3][i];
+          if (ky == 0) d = make_float2(x[i].x * w[0].x, x[i].y * w[0].y);
+          else { d.x = fmaf(x[i].x, w[ky * 3].x, d.x); d.y = fmaf(x[i].y, w[ky * 3].y, d.y); }
+          d.x = fmaf(x[i + 1].x, w[ky * 3 + 1].x, d.x); d.y = fmaf(x[i + 1].y, w[ky * 3 + 1].y, d.y);
+          d.x = fmaf(x[i + 2].x, w[ky * 3 + 2].x, d.x); d.y = fmaf(x[i + 2].y, w[ky * 3 + 2].y, d.y);
+        }
+      }
+      if (j >= 2 && j - 2 < th) {
+        uint32_t* o = orow0 + ((size_t)(j - 2) * p.OW + cx) * opitch;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < ncol) o[(size_t)i * opitch] = pack2<T>(acc[(j - 2) % 3][i].x, acc[(j - 2) % 3][i].y);
+      }
+    }
+  }
+}
+
+bool dw_tile_supported(const DwParams& p, int et) {
+  return dw_strip_supported(p, et) && p.rate == 1;
+}
+
+cudaError_t launch_dw_tile(const DwParams& p, int et, cudaStream_t s) {
+  const int nchunks = (p.in.C + 63) / 64, tiles_x = (p.OW + kTileT - 1) / kTileT, tiles_y = (p.OH + kTileT - 1) / kTileT;
+  const long long n_items = (long long)p.N * tiles_y * tiles_x * nchunks;
+  const unsigned blocks = (unsigned)((n_items + 7) / 8);
+  const size_t smem = 8 * (size_t)kTileWarpBytes;      // 100 KB: two blocks per SM
+  static bool attr_done[2] = {false, false};
+  if (et == ET_BF16) {
+    if (!attr_done[0]) { cudaFuncSetAttribute(dw_tile_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done[0] = true; }
+    dw_tile_kernel<__nv_bfloat16><<<blocks, 256, smem, s>>>(p, nchunks, tiles_x, tiles_y, n_items);
+  } else {
+    if (!attr_done[1]) { cudaFuncSetAttribute(dw_tile_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done[1] = true; }
+    dw_tile_kernel<__half><<<blocks, 256, smem, s>>>(p, nchunks, tiles_x, tiles_y, n_items);
+  }
+  return cudaGetLastError();
+}
+
 template <typename TI, typename TO>
 static cudaError_t launch_dw_t(const DwParams& p, cudaStream_t s) {
   const int C = p.in.C;

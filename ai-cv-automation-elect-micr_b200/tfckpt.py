@@ -240,9 +240,28 @@ def params_from_variables(variables, variant="A", scope="nn", strict=True):
     return (params, problems) if not strict else params
 
 
-def load_params(checkpoint_loc, variant="A", scope="nn"):
-    """Denoiser(checkpoint_loc=<directory or prefix>) : latest checkpoint of a directory, or an explicit prefix."""
+def _prefix_of(checkpoint_loc):
     prefix = latest_checkpoint(checkpoint_loc) if os.path.isdir(checkpoint_loc) else checkpoint_loc
     if prefix is None or not os.path.exists(prefix + ".index"):
         raise FileNotFoundError(f"no TensorFlow checkpoint at {checkpoint_loc}")
-    return params_from_variables(read_checkpoint(prefix), variant, scope)
+    return prefix
+
+
+def load_params(checkpoint_loc, variant="A", scope="nn", strict=True):
+    """Denoiser(checkpoint_loc=<directory or prefix>) : latest checkpoint of a directory, or an explicit prefix.
+    ``strict=False`` returns (params, problems) instead of raising on missing / mis-shaped variables."""
+    return params_from_variables(read_checkpoint(_prefix_of(checkpoint_loc)), variant, scope, strict)
+
+
+def diagnose(checkpoint_loc, scope="nn"):
+    """For the first real checkpoint someone tries (the variable naming here is TF-1's documented scope uniquifier applied to
+    the reference's creation order, unverified against a real file -- DESIGN.md): how the checkpoint's variables line up with
+    each graph variant.  Returns {variant: {"problems": [...], "unused": [checkpoint variables the graph did not ask for]}}."""
+    variables = read_checkpoint(_prefix_of(checkpoint_loc))
+    report = {}
+    for variant in ("A", "B"):
+        _, problems = params_from_variables(variables, variant, scope, strict=False)
+        wanted = {t for t, _ in tf_variable_names(variant, scope)}
+        unused = sorted(v for v in variables if v not in wanted and "Momentum" not in v and v != "global_step")
+        report[variant] = {"problems": problems, "unused": unused}
+    return report

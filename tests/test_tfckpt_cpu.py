@@ -79,3 +79,23 @@ def test_mismatches_are_reported(emd, tmp_path):
     open(tmp_path / "junk.index", "wb").write(b"\x00" * 100)
     with pytest.raises(ValueError, match="bad table magic"):
         emd.tfckpt.read_index(str(tmp_path / "junk.index"))
+
+
+def test_diagnose_reports_mismatches_per_variant(tmp_path):
+    """tfckpt.diagnose: a variant-A checkpoint lines up with graph A and reports what graph B would miss; strict=False returns the
+    problem list instead of raising (what to run on the first real checkpoint)."""
+    import importlib
+    emd = importlib.import_module("ai-cv-automation-elect-micr_b200")
+    params = emd.weights.init_reference_weights(0)
+    variables = {t: params[p] for t, p in emd.tfckpt.tf_variable_names("A")}
+    variables["nn/extra/unrelated"] = np.zeros(3, np.float32)
+    del variables[next(t for t, p in emd.tfckpt.tf_variable_names("A") if p == "mid3_1/pw")]
+    write_checkpoint(str(tmp_path / "model.ckpt-3"), variables)
+    rep = emd.tfckpt.diagnose(str(tmp_path))
+    assert len(rep["A"]["problems"]) == 1 and "mid3_1/pw" in rep["A"]["problems"][0]
+    assert rep["A"]["unused"] == ["nn/extra/unrelated"]
+    assert len(rep["B"]["problems"]) > 3
+    got, problems = emd.tfckpt.load_params(str(tmp_path), "A", strict=False)
+    assert len(problems) == 1 and "mid3_0/pw" in got and "mid3_1/pw" not in got
+    with pytest.raises(ValueError, match="does not match the graph"):
+        emd.tfckpt.load_params(str(tmp_path), "A")
