@@ -149,6 +149,7 @@ struct Tuning {
   int sliced_io = 1;       // EMD_DISABLE_SLICED_IO: host-buffer passes as the two-chunk pipeline
   int halves = 1;          // EMD_DISABLE_HALVES: no half-batch head / tail in host-buffer passes
   int mid_graph = 1;       // EMD_DISABLE_MID_GRAPH: no graph replay of the whole-batch middle section
+  int skip_taps = 1;       // EMD_DISABLE_SKIP_TAPS: dilated / transposed convs multiply every tap on every tile, padding or not
   int dw_tile = 1;         // EMD_DISABLE_DW_TILE: small-map depthwise on the strip kernel (no shared-memory staging)
   int dw_strip = 1;        // EMD_DISABLE_DW_STRIP: small-map / dilated depthwise on the one-thread-per-pixel kernel
   int dw_cols = 1;         // EMD_DISABLE_DW_COLS: depthwise producer with one pixel column per thread (first form)

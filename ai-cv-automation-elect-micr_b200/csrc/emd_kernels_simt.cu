@@ -8,6 +8,7 @@
 //  * dw3x3_kernel: depthwise 3x3 (stride / rate in the depthwise stage, App. A.2), memory-bound.
 //  * resize / avgpool / cast: memory-bound helpers (DMG:331-345, 494).
 #include "emd_kernels.h"
+#include "emd_tma.h"
 
 namespace emd {
 
@@ -407,9 +408,9 @@ cudaError_t launch_dw_strip(const DwParams& p, int et, cudaStream_t s) {
 // per instruction, ~100 loads in flight per warp and no registers held -- the strip kernel's nine loads in flight per warp left
 // it latency-bound at 0.3 of the HBM roofline, and re-read every column three times), then slides the 3x3 window over it in
 // passes of four columns (the thread mapping of the fused kernel's depthwise producer).  Same tap order as the other kernels.
-constexpr int kTileT = 8, kTileHalo = kTileT + 2, kTileWarpBytes = kTileHalo * kTileHalo * 128;
+constexpr int kTileT = 8;
 template <typename T>
-__global__ void __launch_bounds__(256) dw_tile_kernel(const DwParams p, int nchunks, int tiles_x, int tiles_y, long long n_items) {
+__global__ void __launch_bounds__(256) dw_tile_kernel(const DwParams p, int nchunks, int tiles_x, int tiles_y, long long n_items, int hw, int warp_bytes) {
   extern __shared__ __align__(16) uint8_t tile_smem[];
   const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (item >= n_items) return;
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(256) dw_tile_kernel(const DwParams p, int nchu
   const uint32_t* gin = reinterpret_cast<const uint32_t*>(reinterpret_cast<const T*>(p.in.ptr) + p.in.coff);
   uint32_t* gout = reinterpret_cast<uint32_t*>(reinterpret_cast<T*>(p.out.ptr) + p.out.coff);
   const int ipitch = p.in.pitch >> 1, opitch = p.out.pitch >> 1;
-  uint32_t* sm = reinterpret_cast<uint32_t*>(tile_smem + (size_t)wib * kTileWarpBytes) + lane;      // [halo pixel][32 lanes]
+  uint32_t* sm = reinterpret_cast<uint32_t*>(tile_smem + (size_t)wib * warp_bytes) + lane;      // [halo pixel (row pitch hw)][32 lanes]
   const uint32_t sm_addr = (uint32_t)__cvta_generic_to_shared(sm);
   // halo in: one cp.async per in-bounds halo pixel, zeros elsewhere (TF SAME padding)
   const uint32_t* img = gin + ((size_t)n * H * W) * ipitch + cw;
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(256) dw_tile_kernel(const DwParams p, int nchu
     const bool y_ok = y >= 0 && y < H;
     for (int hx = 0; hx < tw + 2; ++hx) {
       const int x = x0 - 1 + hx;
-      const int slot = hy * kTileHalo + hx;
+      const int slot = hy * hw + hx;
       if (ch_ok && y_ok && x >= 0 && x < W)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sm_addr + (uint32_t)slot * 128u), "l"(img + ((size_t)y * W + x) * ipitch) : "memory");
       else
@@ -455,11 +456,11 @@ __global__ void __launch_bounds__(256) dw_tile_kernel(const DwParams p, int nchu
     const int ncol = min(4, tw - cx);
     float2 acc[3][4];
 #pragma unroll
-    for (int j = 0; j < kTileHalo; ++j) {           // halo rows y0 - 1 + j
+    for (int j = 0; j < kTileT + 2; ++j) {          // halo rows y0 - 1 + j
       if (j >= th + 2) break;
       float2 x[6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) x[i] = (i < ncol + 2) ? unpack2<T>(sm[(j * kTileHalo + cx + i) * 32]) : make_float2(0.f, 0.f);
+      for (int i = 0; i < 6; ++i) x[i] = (i < ncol + 2) ? unpack2<T>(sm[(j * hw + cx + i) * 32]) : make_float2(0.f, 0.f);
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int r = j - ky;
@@ -467,10 +468,9 @@ __global__ void __launch_bounds__(256) dw_tile_kernel(const DwParams p, int nchu
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float2& d = acc[r % 3][i];
-          if (ky == 0) d = make_float2(x[i].x * w[0].x, x[i].y * w[0].y);
-          else { d.x = fmaf(x[i].x, w[ky * 3].x, d.x); d.y = fmaf(x[i].y, w[ky * 3].y, d.y); }
-          d.x = fmaf(x[i + 1].x, w[ky * 3 + 1].x, d.x); d.y = fmaf(x[i + 1].y, w[ky * 3 + 1].y, d.y);
-          d.x = fmaf(x[i + 2].x, w[ky * 3 + 2].x, d.x); d.y = fmaf(x[i + 2].y, w[ky * 3 + 2].y, d.y);
+          d = ky == 0 ? ptx::fmul2(x[i], w[0]) : ptx::ffma2(x[i], w[ky * 3], d);
+          d = ptx::ffma2(x[i + 1], w[ky * 3 + 1], d);
+          d = ptx::ffma2(x[i + 2], w[ky * 3 + 2], d);
         }
       }
       if (j >= 2 && j - 2 < th) {
@@ -491,14 +491,19 @@ cudaError_t launch_dw_tile(const DwParams& p, int et, cudaStream_t s) {
   const int nchunks = (p.in.C + 63) / 64, tiles_x = (p.OW + kTileT - 1) / kTileT, tiles_y = (p.OH + kTileT - 1) / kTileT;
   const long long n_items = (long long)p.N * tiles_y * tiles_x * nchunks;
   const unsigned blocks = (unsigned)((n_items + 7) / 8);
-  const size_t smem = 8 * (size_t)kTileWarpBytes;      // 100 KB: two blocks per SM
+  // the halo buffer is sized for THIS map (6 x 6 maps: 8 x 8 pixels = 8 KB per warp, three blocks of eight warps per SM; 24 x 24:
+  // 10 x 10 = 12.5 KB, two blocks): residency is what hides the load phase of one warp under the math of the others
+  const int hw = (p.OW < kTileT ? p.OW : kTileT) + 2, hh = (p.OH < kTileT ? p.OH : kTileT) + 2;
+  const int warp_bytes = hw * hh * 128;
+  const size_t smem = 8 * (size_t)warp_bytes;
   static bool attr_done[2] = {false, false};
+  const size_t smem_max = 8 * (size_t)(kTileT + 2) * (kTileT + 2) * 128;
   if (et == ET_BF16) {
-    if (!attr_done[0]) { cudaFuncSetAttribute(dw_tile_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done[0] = true; }
-    dw_tile_kernel<__nv_bfloat16><<<blocks, 256, smem, s>>>(p, nchunks, tiles_x, tiles_y, n_items);
+    if (!attr_done[0]) { cudaFuncSetAttribute(dw_tile_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max); attr_done[0] = true; }
+    dw_tile_kernel<__nv_bfloat16><<<blocks, 256, smem, s>>>(p, nchunks, tiles_x, tiles_y, n_items, hw, warp_bytes);
   } else {
-    if (!attr_done[1]) { cudaFuncSetAttribute(dw_tile_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done[1] = true; }
-    dw_tile_kernel<__half><<<blocks, 256, smem, s>>>(p, nchunks, tiles_x, tiles_y, n_items);
+    if (!attr_done[1]) { cudaFuncSetAttribute(dw_tile_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max); attr_done[1] = true; }
+    dw_tile_kernel<__half><<<blocks, 256, smem, s>>>(p, nchunks, tiles_x, tiles_y, n_items, hw, warp_bytes);
   }
   return cudaGetLastError();
 }

@@ -20,6 +20,7 @@ const Entry kTable[] = {
     {"sliced_io", "EMD_DISABLE_SLICED_IO", &Tuning::sliced_io, true},
     {"halves", "EMD_DISABLE_HALVES", &Tuning::halves, true},
     {"mid_graph", "EMD_DISABLE_MID_GRAPH", &Tuning::mid_graph, true},
+    {"skip_taps", "EMD_DISABLE_SKIP_TAPS", &Tuning::skip_taps, true},
     {"dw_tile", "EMD_DISABLE_DW_TILE", &Tuning::dw_tile, true},
     {"dw_strip", "EMD_DISABLE_DW_STRIP", &Tuning::dw_strip, true},
     {"dw_cols", "EMD_DISABLE_DW_COLS", &Tuning::dw_cols, true},
