@@ -419,7 +419,7 @@ def main():
                       "bit_identical_to_single_gpu": bool(identical) if rank == 0 else None}
         del seng
 
-    if rank == 0 and not args.no_configs:
+    if rank == 0 and not args.no_configs and world == 1:      # single-GPU configs: reported at N=1 only (the other ranks would idle)
         # ---- configs[2]: one 2048x2048 micrograph, 25 crops ----
         meng = emd.Engine(device=local, cropsize=S, max_batch=25)
         meng.set_option("strict", 1)
@@ -462,8 +462,9 @@ def main():
             if mode == args.mode:
                 modes[mode] = B * args.steps / (ms * 1e-3)
                 continue
-            t_ms, _ = timed(lambda i, mode=mode: eng.forward(dev_sets[i % n_sets], out=d_out, mode=mode, stream=stream), steps, 2)
-            modes[mode] = B * steps / (t_ms * 1e-3)
+            # (not timed(): that one is collective; this section runs on one rank only)
+            t_ms = wall(lambda mode=mode: eng.forward(dev_sets[0], out=d_out, mode=mode, stream=stream), reps=steps, warm=2)
+            modes[mode] = B / (t_ms * 1e-3)
         configs["crops_per_s_by_mode"] = modes
         # ---- configs[4]: 96x96 crops at batch 4096 (small_scans shape) ----
         del eng
