@@ -30,6 +30,7 @@ SIGNATURES = {
     "emd_forward": (_I, [_P, _P, _I, _P, _I, _P]),
     "emd_plan_tiles": (_I, [_I, _I, _I, _I, _IP, _IP, _IP, _IP]),
     "emd_normalise": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "emd_preprocess_crop": (_I, [_P, _P, _I, _I, _P, _P]),
     "emd_gather_crops": (_I, [_P, _P, _I, _I, _IP, _IP, _I, _I, _I, _P, _P]),
     "emd_stitch": (_I, [_P, _P, _IP, _IP, _I, _I, _I, _I, _I, _I, _P, _P]),
     "emd_denoise_image": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),

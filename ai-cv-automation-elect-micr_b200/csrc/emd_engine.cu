@@ -1396,6 +1396,33 @@ int emd_denoise_stream(emd_engine* e, const void* const* imgs, int count, int H,
   return denoise_images(e, imgs, count, H, W, overlap, flags, mode, outs, stream ? (cudaStream_t)stream : e->stream);
 }
 
+int emd_preprocess_crop(emd_engine* e, const float* img, int H, int W, float* out, void* stream) {
+  if (!e || !img || !out || H < 1 || W < 1) return EMD_EINVAL;
+  CU(e, cudaSetDevice(e->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  const int S = e->S;
+  const size_t n_in = (size_t)H * W * 4, n_out = (size_t)S * S * 4;
+  int rc;
+  const float* d_src = img;
+  if (!is_device_ptr(img)) {
+    if ((rc = grow(e, reinterpret_cast<char**>(&e->d_img_raw), &e->img_raw_bytes, n_in))) return rc;
+    CU(e, cudaMemcpyAsync(e->d_img_raw, img, n_in, cudaMemcpyHostToDevice, s));
+    d_src = reinterpret_cast<const float*>(e->d_img_raw);
+  }
+  if ((rc = grow(e, &e->d_img, &e->img_bytes, 2 * n_out + 64))) return rc;      // [tmp][out][4 floats of min / max]
+  float* d_tmp = e->d_img;
+  const bool out_dev = is_device_ptr(out);
+  float* d_out = out_dev ? out : e->d_img + (size_t)S * S;
+  float* d_mm = e->d_img + 2 * (size_t)S * S;
+  CU(e, launch_preprocess_crop(d_src, H, W, S, d_tmp, d_mm, d_out, s));
+  e->cnt.launches += 5;
+  if (!out_dev) {
+    CU(e, cudaMemcpyAsync(out, d_out, n_out, cudaMemcpyDeviceToHost, s));
+    CU(e, cudaStreamSynchronize(s));
+  }
+  return EMD_OK;
+}
+
 int emd_set_keep_activations(emd_engine* e, int keep) {
   if (!e) return EMD_EINVAL;
   CU(e, cudaSetDevice(e->device));

@@ -183,5 +183,7 @@ cudaError_t launch_gather(const float* img, int H, int W, const int* d_ys, const
 cudaError_t launch_stitch(const float* tiles, const int* d_ys, const int* d_xs, int ny, int nx, int crop, int H,
                           int W, int clip, void* out /* double*, or float* with out_f32 */, int out_f32, cudaStream_t s);
 size_t minmax_partial_bytes();
+// Denoiser.preprocess (DEN:632-643) on the device: resize to S x S, scale0to1, NaN/Inf -> 0.5, scale0to1; d_tmp [S*S], d_mm [4] floats
+cudaError_t launch_preprocess_crop(const float* d_img, int H, int W, int S, float* d_tmp, float* d_mm, float* d_out, cudaStream_t s);
 
 }  // namespace emd

@@ -91,6 +91,72 @@ cudaError_t launch_normalise_apply(const void* img, int in_f64, size_t n, const 
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Denoiser.preprocess (DEN:632-643), the single-crop path: cv2.resize to S x S (INTER_LINEAR: half-pixel centres, edge
+// replicate, float coefficients, horizontal pass then vertical), scale0to1, NaN -> 0.5, Inf -> 0.5, scale0to1.  The FIRST
+// min-max runs before the NaN/Inf replacement: numpy's min/max propagate NaN, so one NaN flattens the crop.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resize_linear_kernel(const float* __restrict__ img, int H, int W, int S, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * S) return;
+  const int oy = idx / S, ox = idx - oy * S;
+  if (H == S && W == S) { out[idx] = img[idx]; return; }            // cv2 copies when the size does not change
+  const double fy = ((double)oy + 0.5) * ((double)H / S) - 0.5, fx = ((double)ox + 0.5) * ((double)W / S) - 0.5;
+  const int y0 = (int)floor(fy), x0 = (int)floor(fx);
+  const float wy = (float)(fy - y0), wx = (float)(fx - x0);
+  const int y0c = min(max(y0, 0), H - 1), y1c = min(max(y0 + 1, 0), H - 1), x0c = min(max(x0, 0), W - 1), x1c = min(max(x0 + 1, 0), W - 1);
+  const float a0 = __fsub_rn(1.0f, wx), b0 = __fsub_rn(1.0f, wy);
+  const float r0 = __fadd_rn(__fmul_rn(img[(size_t)y0c * W + x0c], a0), __fmul_rn(img[(size_t)y0c * W + x1c], wx));
+  const float r1 = __fadd_rn(__fmul_rn(img[(size_t)y1c * W + x0c], a0), __fmul_rn(img[(size_t)y1c * W + x1c], wx));
+  out[idx] = __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, wy));
+}
+
+// numpy-style min / max of a small array (one block): result NaN if any element is NaN.  mm = {min, max}
+__global__ void __launch_bounds__(1024) minmax_numpy_kernel(const float* __restrict__ x, int n, float* __restrict__ mm) {
+  float mn = INFINITY, mx = -INFINITY;
+  int nan = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = x[i];
+    if (isnan(v)) nan = 1;
+    else { mn = fminf(mn, v); mx = fmaxf(mx, v); }
+  }
+  __shared__ float smn[32], smx[32];
+  __shared__ int snan;
+  if (threadIdx.x == 0) snan = 0;
+  __syncthreads();
+  if (nan) atomicOr(&snan, 1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+  if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
+    mm[0] = snan ? NAN : mn;
+    mm[1] = snan ? NAN : mx;
+  }
+}
+
+// scale0to1 as numpy computes it on float32 (NaN / Inf propagate through the IEEE sub / div), optionally followed by the
+// NaN -> 0.5, Inf -> 0.5 replacement of DEN:638-639
+__global__ void __launch_bounds__(256) scale0to1_kernel(const float* __restrict__ x, int n, const float* __restrict__ mm, int fix, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float mn = mm[0], mx = mm[1];
+  float v = (mn == mx) ? 0.5f : __fdiv_rn(__fsub_rn(x[i], mn), __fsub_rn(mx, mn));     // NaN == NaN is false: falls to the division, like numpy
+  if (fix && (isnan(v) || isinf(v))) v = 0.5f;
+  out[i] = v;
+}
+
+cudaError_t launch_preprocess_crop(const float* d_img, int H, int W, int S, float* d_tmp, float* d_mm, float* d_out, cudaStream_t s) {
+  const int n = S * S, blocks = (n + 255) / 256;
+  resize_linear_kernel<<<blocks, 256, 0, s>>>(d_img, H, W, S, d_out);
+  minmax_numpy_kernel<<<1, 1024, 0, s>>>(d_out, n, d_mm);
+  scale0to1_kernel<<<blocks, 256, 0, s>>>(d_out, n, d_mm, 1, d_tmp);
+  minmax_numpy_kernel<<<1, 1024, 0, s>>>(d_tmp, n, d_mm + 2);
+  scale0to1_kernel<<<blocks, 256, 0, s>>>(d_tmp, n, d_mm + 2, 0, d_out);
+  return cudaGetLastError();
+}
+
 // crops[(i*nx+j), r, c] = img[ys[i]+r, xs[j]+c]; one thread per 4 output pixels (crop % 4 == 0)
 __global__ void __launch_bounds__(256) gather_kernel(const float* __restrict__ img, int H, int W,
                                                      const int* __restrict__ ys, const int* __restrict__ xs, int ny,

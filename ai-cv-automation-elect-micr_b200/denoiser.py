@@ -106,8 +106,10 @@ class Denoiser(object):
         self.engine.load_weights(blob)
 
     def preprocess(self, img):
-        """DEN:632-643: resize to the crop size, scale0to1, NaN/Inf -> 0.5, scale0to1, reshape."""
-        return preprocess_crop(img, self.cropsize)
+        """DEN:632-643: resize to the crop size, scale0to1, NaN/Inf -> 0.5, scale0to1, reshape -- on the GPU
+        (``emd_preprocess_crop``; ``preprocess_crop`` in this module is the same thing on the host)."""
+        s = self.cropsize
+        return self.engine.preprocess_crop(np.asarray(img)).reshape(1, s, s, 1)
 
     def denoise_crop(self, img, preprocess=True, postprocess=True):
         """DEN:645-651: one forward pass.  Returns (S,S) clipped if postprocess, else the raw

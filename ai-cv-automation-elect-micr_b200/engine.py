@@ -159,6 +159,23 @@ class Engine:
                                            img.shape[1], _ptr(out), None), "emd_normalise")
         return out
 
+    def preprocess_crop(self, img, out=None):
+        """Denoiser.preprocess (DEN:632-643) on the GPU: img [H,W] float32 (numpy / torch host or CUDA) -> [S,S] float32."""
+        if len(img.shape) != 2:
+            raise ValueError(f"preprocess_crop expects a 2-D image, got shape {tuple(img.shape)}")
+        img = _dense(img, "img")
+        if out is None:
+            if isinstance(img, np.ndarray):
+                out = np.empty((self.S, self.S), np.float32)
+            else:
+                import torch
+                out = torch.empty((self.S, self.S), dtype=torch.float32, device=img.device)
+        else:
+            _check_out(out, "out", "float32", (self.S, self.S))
+        self._check(self.lib.emd_preprocess_crop(self.h, _ptr(img), int(img.shape[0]), int(img.shape[1]), _ptr(out),
+                                                 _stream_for(img, None)), "emd_preprocess_crop")
+        return out
+
     def gather_crops(self, img, ys, xs, crop=None):
         crop = crop or self.S
         img = np.ascontiguousarray(img, np.float32)

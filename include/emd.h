@@ -86,6 +86,12 @@ int emd_plan_tiles(int H, int W, int crop, int overlap, int* ys, int* xs, int* n
  * image -> 0.5, result cast to f32.  in_f64 != 0: img is const double*. */
 int emd_normalise(emd_engine* e, const void* img, int in_f64, int H, int W, float* out, void* stream);
 
+/* Replaces Denoiser.preprocess (DEN:632-643), the single-crop path of denoise_crop(preprocess=True): img [H,W] f32 (host or device)
+ * -> out [S,S] f32: cv2.resize to the crop size (INTER_LINEAR arithmetic: half-pixel centres, edge replicate, float
+ * coefficients), scale0to1, NaN -> 0.5, Inf -> 0.5, scale0to1 -- in the class file's order: the first min-max runs BEFORE the
+ * NaN/Inf replacement and propagates NaN like numpy. */
+int emd_preprocess_crop(emd_engine* e, const float* img, int H, int W, float* out, void* stream);
+
 /* Replaces the crop slicing of DEN:671-673: img [H,W] f32 -> crops [ny*nx,crop,crop] f32, row-major
  * over (i,j) like the reference's double loop. */
 int emd_gather_crops(emd_engine* e, const float* img, int H, int W, const int* ys, const int* xs,
