@@ -1101,8 +1101,8 @@ int emd_forward(emd_engine* e, const float* crops, int n, float* out, int mode, 
   CU(e, cudaEventRecord(e->ev_start, s));          // work already queued on the caller's stream comes first
   CU(e, cudaStreamWaitEvent(e->copy_in, e->ev_start, 0));
   CU(e, cudaStreamWaitEvent(e->copy_out, e->ev_start, 0));
-  const bool sliceable = tuning().sliced_io &&   // A/B switch: the two-chunk pipeline below !e->profile && !e->keep && e->steps.size() >= 3 && e->steps.front().in.t == e->t_input &&
-                         e->steps.back().out.t == e->t_output && e->steps.back().in.t != e->t_input;
+  const bool sliceable = tuning().sliced_io /* A/B switch: the two-chunk pipeline below */ && !e->profile && !e->keep && e->steps.size() >= 3 &&
+                         e->steps.front().in.t == e->t_input && e->steps.back().out.t == e->t_output && e->steps.back().in.t != e->t_input;
   if (sliceable && n >= 16 && e->max_batch >= 16) {
     // passes of up to max_batch crops (balanced, so that no pass is a small remainder)
     const int npass = (n + e->max_batch - 1) / e->max_batch, pb = (n + npass - 1) / npass;

@@ -671,9 +671,12 @@ __global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
     const long long pix = pix0 + threadIdx.x;
     float d = 0.f;
     if (pix < npix) {
-      const int ox = (int)(pix % OW);
-      const long long r = pix / OW;
-      const int oy = (int)(r % OH), n = (int)(r / OH);
+      // 32-bit index arithmetic (the launcher guarantees npix < 2^31): three 64-bit divisions per thread were a visible part of
+      // this write-bound kernel's instruction stream
+      const unsigned upix = (unsigned)pix;
+      const int ox = (int)(upix % (unsigned)OW);
+      const unsigned r = upix / (unsigned)OW;
+      const int oy = (int)(r % (unsigned)OH), n = (int)(r / (unsigned)OH);
       const float* img = p.in + (size_t)n * p.IH * p.IW;
       if (p.dw) {
 #pragma unroll
@@ -722,7 +725,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
 cudaError_t launch_stem(const StemParams& p, int et, cudaStream_t s) {
   const long long npix = (long long)p.N * p.out.H * p.out.W;
   const int cg = p.out.C >> 3;
-  if (cg < 1 || cg > 256 || (cg & (cg - 1))) return cudaErrorInvalidValue;
+  if (cg < 1 || cg > 256 || (cg & (cg - 1)) || npix >= (1ll << 31)) return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)((npix + 255) / 256);
   if (et == ET_F32) stem_kernel<float><<<grid, 256, 0, s>>>(p);
   else if (et == ET_BF16) stem_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p);
