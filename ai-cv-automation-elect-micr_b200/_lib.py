@@ -28,6 +28,8 @@ SIGNATURES = {
     "emd_destroy": (_I, [_P]),
     "emd_load_weights": (_I, [_P, _P, _SZ]),
     "emd_forward": (_I, [_P, _P, _I, _P, _I, _P]),
+    "emd_forward_async": (_I, [_P, _P, _I, _P, _I, _P]),
+    "emd_synchronize": (_I, [_P, _P]),
     "emd_plan_tiles": (_I, [_I, _I, _I, _I, _IP, _IP, _IP, _IP]),
     "emd_normalise": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "emd_preprocess_crop": (_I, [_P, _P, _I, _I, _P, _P]),

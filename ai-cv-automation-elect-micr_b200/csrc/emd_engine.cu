@@ -87,6 +87,8 @@ struct emd_engine {
   float *d_stage_in = nullptr, *d_stage_out = nullptr;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of emd_forward with host buffers
   cudaEvent_t ev_in[2] = {}, ev_done[2] = {}, ev_out[2] = {}, ev_start = nullptr;
+  bool chained = false;                                   // an emd_forward_async call is outstanding: the next one pipelines behind it
+  cudaStream_t chain_stream = nullptr;                    // ... on this compute stream
   int last_input_step = 0;                                // last step that reads the network input
   int head_end = -1, tail_start = 1 << 30;                // half-batch phases of the host-buffer pass (plan_arena)
   static constexpr int kSlices = 8;                       // sliced first / last step of a pass (emd_forward, host buffers)
@@ -141,6 +143,16 @@ int fail(emd_engine* e, int code, const char* fmt, ...) {
     if (_r != cudaSuccess)                                                                  \
       return fail(e, EMD_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_r), __FILE__, __LINE__); \
   } while (0)
+
+// Outstanding emd_forward_async calls share the workspace and the staging buffers with everything else the engine does: any
+// other entry point (or an async call on another stream) first waits for them.
+int drain_chain(emd_engine* e) {
+  if (!e->chained) return EMD_OK;
+  CU(e, cudaStreamSynchronize(e->chain_stream));
+  if (e->copy_out) CU(e, cudaStreamSynchronize(e->copy_out));
+  e->chained = false;
+  return EMD_OK;
+}
 
 bool is_device_ptr(const void* p) {
   cudaPointerAttributes a;
@@ -1041,6 +1053,7 @@ int emd_load_weights(emd_engine* e, const void* blob, size_t nbytes) {
     entries[r.name] = BlobEntry{r.rows, r.cols, (size_t)r.offset};
   }
   // from here on the old weights are gone: the engine is unusable until the new ones are bound
+  { int drc = drain_chain(e); if (drc) return drc; }
   CU(e, cudaStreamSynchronize(e->stream));
   e->weights_loaded = false;
   drop_graphs(e);
@@ -1061,7 +1074,7 @@ int emd_load_weights(emd_engine* e, const void* blob, size_t nbytes) {
   return EMD_OK;
 }
 
-int emd_forward(emd_engine* e, const float* crops, int n, float* out, int mode, void* stream) {
+static int forward_impl(emd_engine* e, const float* crops, int n, float* out, int mode, void* stream, bool async) {
   if (!e || !crops || !out || n < 0) return EMD_EINVAL;
   int rc = check_mode(e, mode);
   if (rc) return rc;
@@ -1069,6 +1082,7 @@ int emd_forward(emd_engine* e, const float* crops, int n, float* out, int mode, 
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
   const bool in_dev = is_device_ptr(crops), out_dev = is_device_ptr(out);
   const size_t per = (size_t)e->S * e->S;
+  if (e->chained && (s != e->chain_stream || (in_dev && out_dev)) && (rc = drain_chain(e))) return rc;
   if (in_dev && out_dev) {
     for (int c0 = 0; c0 < n; c0 += e->max_batch) {
       const int nb = std::min(e->max_batch, n - c0);
@@ -1098,9 +1112,12 @@ int emd_forward(emd_engine* e, const float* crops, int n, float* out, int mode, 
     CU(e, cudaEventCreateWithFlags(&e->ev_in_free, cudaEventDisableTiming));
     CU(e, cudaEventCreateWithFlags(&e->ev_out_free, cudaEventDisableTiming));
   }
-  CU(e, cudaEventRecord(e->ev_start, s));          // work already queued on the caller's stream comes first
-  CU(e, cudaStreamWaitEvent(e->copy_in, e->ev_start, 0));
-  CU(e, cudaStreamWaitEvent(e->copy_out, e->ev_start, 0));
+  const bool chained = e->chained;                 // pipelining behind an outstanding async call: its events already order the staging buffers
+  if (!chained) {
+    CU(e, cudaEventRecord(e->ev_start, s));        // work already queued on the caller's stream comes first
+    CU(e, cudaStreamWaitEvent(e->copy_in, e->ev_start, 0));
+    CU(e, cudaStreamWaitEvent(e->copy_out, e->ev_start, 0));
+  }
   const bool sliceable = tuning().sliced_io /* A/B switch: the two-chunk pipeline below */ && !e->profile && !e->keep && e->steps.size() >= 3 &&
                          e->steps.front().in.t == e->t_input && e->steps.back().out.t == e->t_output && e->steps.back().in.t != e->t_input;
   if (sliceable && n >= 16 && e->max_batch >= 16) {
@@ -1110,13 +1127,16 @@ int emd_forward(emd_engine* e, const float* crops, int n, float* out, int mode, 
       const int nb = std::min(pb, n - c0);
       if ((rc = run_network_sliced(e, in_dev ? nullptr : crops + c0 * per, out_dev ? nullptr : out + c0 * per,
                                    in_dev ? crops + c0 * per : e->d_stage_in, out_dev ? out + c0 * per : e->d_stage_out, nb, mode, s,
-                                   ip == 0)))
+                                   ip == 0 && !chained)))
         return rc;
     }
+    if (async) { e->chained = true; e->chain_stream = s; return EMD_OK; }        // emd_synchronize waits
     CU(e, cudaStreamSynchronize(s));
     if (!out_dev) CU(e, cudaStreamSynchronize(e->copy_out));
+    e->chained = false;
     return EMD_OK;
   }
+  if (chained && (rc = drain_chain(e))) return rc;   // a different path follows an async chain: drain it first
   for (int i = 0; i < nchunks; ++i) {
     const int c0 = i * ch, nb = std::min(ch, n - c0), slot = i % nslots;
     const float* d_in = crops + c0 * per;
@@ -1143,6 +1163,25 @@ int emd_forward(emd_engine* e, const float* crops, int n, float* out, int mode, 
   }
   CU(e, cudaStreamSynchronize(s));
   if (!out_dev) CU(e, cudaStreamSynchronize(e->copy_out));
+  return EMD_OK;
+}
+
+int emd_forward(emd_engine* e, const float* crops, int n, float* out, int mode, void* stream) {
+  return forward_impl(e, crops, n, out, mode, stream, false);
+}
+
+int emd_forward_async(emd_engine* e, const float* crops, int n, float* out, int mode, void* stream) {
+  return forward_impl(e, crops, n, out, mode, stream, true);
+}
+
+int emd_synchronize(emd_engine* e, void* stream) {
+  if (!e) return EMD_EINVAL;
+  CU(e, cudaSetDevice(e->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  int rc = drain_chain(e);
+  if (rc) return rc;
+  CU(e, cudaStreamSynchronize(s));
+  if (e->copy_out) CU(e, cudaStreamSynchronize(e->copy_out));
   return EMD_OK;
 }
 
@@ -1291,6 +1330,7 @@ int emd_quality(emd_engine* e, const float* a, const float* b, int n, int H, int
 // compute stream `s` (network), `post` (stitch, download); image i uses slot i & 1.  One image = the same chain without overlap.
 static int denoise_images(emd_engine* e, const void* const* imgs, int count, int H, int W, int overlap, int flags, int mode,
                           void* const* outs, cudaStream_t s) {
+  { int drc = drain_chain(e); if (drc) return drc; }
   const int crop = e->S;
   if (H < crop || W < crop) return fail(e, EMD_EINVAL, "image %dx%d smaller than the %d crop", H, W, crop);
   if (overlap < 0 || overlap >= crop) return fail(e, EMD_EINVAL, "overlap %d outside [0,%d)", overlap, crop);
@@ -1426,6 +1466,7 @@ int emd_preprocess_crop(emd_engine* e, const float* img, int H, int W, float* ou
 int emd_set_keep_activations(emd_engine* e, int keep) {
   if (!e) return EMD_EINVAL;
   CU(e, cudaSetDevice(e->device));
+  { int drc = drain_chain(e); if (drc) return drc; }
   CU(e, cudaStreamSynchronize(e->stream));
   e->keep = keep != 0;
   return plan_arena(e);
@@ -1475,6 +1516,7 @@ int emd_run_layer(emd_engine* e, const char* name, const float* in, const float*
   int rc = check_mode(e, mode);
   if (rc) return rc;
   if (n < 1 || n > e->max_batch) return fail(e, EMD_EINVAL, "n=%d outside [1,%d]", n, e->max_batch);
+  if ((rc = drain_chain(e))) return rc;
   std::vector<int> idx;
   for (int i = 0; i < (int)e->steps.size(); ++i)
     if (e->steps[i].layer == name) idx.push_back(i);

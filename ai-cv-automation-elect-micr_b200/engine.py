@@ -95,8 +95,11 @@ class Engine:
         self._check(self.lib.emd_load_weights(self.h, C.c_char_p(blob), len(blob)), "emd_load_weights")
 
     # -- network ---------------------------------------------------------------------------
-    def forward(self, crops, out=None, mode="fp16", stream=None):
-        """crops [n,S,S] float32 (numpy, or torch host/CUDA tensor) -> [n,S,S] float32."""
+    def forward(self, crops, out=None, mode="fp16", stream=None, sync=True):
+        """crops [n,S,S] float32 (numpy, or torch host/CUDA tensor) -> [n,S,S] float32.
+        sync=False (host buffers, a stream of batches): return without waiting (emd_forward_async); successive calls pipeline
+        their copies under each other's network passes; call ``synchronize()`` before touching the buffers, and give every
+        outstanding call its own ``out``."""
         n = int(crops.shape[0])
         if len(crops.shape) != 3 or tuple(crops.shape[1:3]) != (self.S, self.S):
             raise ValueError(f"crops must be [n,{self.S},{self.S}], got {tuple(crops.shape)}")
@@ -109,9 +112,16 @@ class Engine:
             else:
                 import torch
                 out = torch.empty((n, self.S, self.S), dtype=torch.float32, device=crops.device)
-        self._check(self.lib.emd_forward(self.h, _ptr(crops), n, _ptr(out), MODES[mode], _stream_for(crops, stream)),
-                    "emd_forward")
+        fn = self.lib.emd_forward if sync else self.lib.emd_forward_async
+        self._check(fn(self.h, _ptr(crops), n, _ptr(out), MODES[mode], _stream_for(crops, stream)), "emd_forward")
+        if not sync:
+            self._inflight = getattr(self, "_inflight", []) + [(crops, out)]       # keep the buffers alive until synchronize()
         return out
+
+    def synchronize(self, stream=None):
+        """Wait for every outstanding ``forward(..., sync=False)`` call (emd_synchronize)."""
+        self._check(self.lib.emd_synchronize(self.h, C.c_void_p(stream) if stream else None), "emd_synchronize")
+        self._inflight = []
 
     def run_layer(self, name, x, res=None, mode="fp32"):
         """One fused layer on NHWC float32 host inputs (parity hook)."""

@@ -279,17 +279,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, units_per_step=1.0):
+    def timed(fn, steps, warmup, finish=None):
         """W untimed calls, then exactly `steps` calls between CUDA events on the launching stream, barrier + synchronize on
-        both sides, max over ranks.  Returns (ms total, kernel launches in the timed region summed over ranks)."""
+        both sides, max over ranks.  `finish` (asynchronous calls): waits for everything outstanding, inside the timed region.
+        Returns (ms total, kernel launches in the timed region summed over ranks)."""
         for i in range(warmup):
             fn(i)
+        if finish:
+            finish()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = eng.kernel_launches
         e0.record()
         for i in range(steps):
             fn(i)
+        if finish:
+            finish()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -306,6 +311,8 @@ def main():
 
     dev_pass = lambda i: eng.forward(dev_sets[i % n_sets], out=d_out, mode=args.mode, stream=stream)
     host_pass = lambda i: eng.forward(host_sets[i % n_sets], out=h_out, mode=args.mode, stream=stream)
+    h_outs = [h_out, torch.empty((B, S, S), dtype=torch.float32).pin_memory()]
+    host_pass_async = lambda i: eng.forward(host_sets[i % n_sets], out=h_outs[i & 1], mode=args.mode, stream=stream, sync=False)
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -327,11 +334,17 @@ def main():
         assert per_pass["conv_cuda_core"] == 0 and per_pass["conv_tcgen05_gen1"] == 0, per_pass
         assert per_pass["conv_fused_pair"] >= 39 and per_pass["conv_fused_dw"] >= 1 and per_pass["final_tcgen05"] == 1, per_pass
 
-    # end to end through the public API with pinned host buffers (H2D + D2H inside the timed region)
-    ms_e2e, _ = timed(host_pass, args.steps, 2)
+    # end to end through the public API with pinned host buffers: every step uploads its own batch and downloads its own result
+    # inside the timed region.  A stream of batches is submitted the way a serving loop would: forward(sync=False) per batch
+    # (emd_forward_async: batch i+1's upload and batch i-1's download run under batch i's pass) and one synchronize() at the end,
+    # inside the timed region; `sync_value` is the same loop with a blocking call per batch.
+    ms_e2e, _ = timed(host_pass_async, args.steps, 2, finish=lambda: eng.synchronize(stream))
+    ms_e2e_sync, _ = timed(host_pass, args.steps, 2)
     clocks = sampler.stop()
     e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-           "h2d_bytes_per_step": B * S * S * 4, "d2h_bytes_per_step": B * S * S * 4}
+           "h2d_bytes_per_step": B * S * S * 4, "d2h_bytes_per_step": B * S * S * 4,
+           "api": "Engine.forward(pinned host in, pinned host out, sync=False) per step + Engine.synchronize() (emd_forward_async / emd_synchronize)",
+           "sync_value": world * B * args.steps / (ms_e2e_sync * 1e-3)}
 
     out = {}
     pk = peaks()

@@ -76,6 +76,14 @@ int emd_load_weights(emd_engine* e, const void* blob, size_t nbytes);
  * in-graph, DMG:534-538). */
 int emd_forward(emd_engine* e, const float* crops, int n, float* out, int mode, void* stream);
 
+/* emd_forward with HOST buffers for a stream of batches (the reference calls sess.run once per crop and waits, DEN:646-647;
+ * there is no counterpart): returns without waiting, the results have landed only after emd_synchronize.  Successive calls
+ * pipeline -- the upload of batch i+1 and the download of batch i-1 run under batch i's network pass.  The caller keeps
+ * `crops` and `out` untouched until emd_synchronize and gives every outstanding call its own `out`.  Same results, bit
+ * for bit, as emd_forward.  (Batches of fewer than 16 crops, or an engine built for fewer, run synchronously.) */
+int emd_forward_async(emd_engine* e, const float* crops, int n, float* out, int mode, void* stream);
+int emd_synchronize(emd_engine* e, void* stream);
+
 /* Tile plan of Denoiser.denoise (DEN:661-669 == TMP:11-19), repaired per SURVEY App. D-2/D-3
  * (integer origins, round-half-to-even, last tile clamped).  Pure integer host code.
  * ys/xs must hold at least H/(crop-overlap)+1 and W/(crop-overlap)+1 ints. */
