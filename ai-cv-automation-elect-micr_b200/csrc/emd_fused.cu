@@ -49,6 +49,7 @@ struct FusedArgs {
   ConvParams p;
   NTiling nt;
   int dw_mode;
+  int dww_bytes;             // dw mode: bytes of the depthwise-weight image in shared memory (nchunks x 9 x 64 floats)
   int skip_taps;             // taps mode: per-tile skipping of taps that fall wholly into the zero padding
   int dw_cols;               // dw mode: depthwise thread mapping (1 = 2 channels x 4 columns x 4 rows, 0 = 4 channels x 1 column x 8 rows)
   int SA, SB, SH, ring;      // taps mode: SA stages of (A + B), SB == SA, SH == 0
@@ -201,7 +202,8 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
   uint8_t* g_halo = smem + (sH - smem_base);
   float* s_scale = reinterpret_cast<float*>(g_halo + (size_t)SH * kHaloBytes);
   float* s_shift = s_scale + kMaxC;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + kMaxC);
+  float* s_dww = s_shift + kMaxC;              // dw mode: depthwise weights as [chunk][tap][64 channels] (a.dww_bytes; 0 in taps mode)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_dww) + a.dww_bytes);
   const uint32_t bar_afull = smem_u32(bars), bar_aempty = bar_afull + 8u * kMaxStages, bar_bfull = bar_aempty + 8u * kMaxStages,
                  bar_bempty = bar_bfull + 8u * kMaxStages, bar_hfull = bar_bempty + 8u * kMaxStages,
                  bar_hempty = bar_hfull + 8u * kMaxStages, bar_tfull = bar_hempty + 8u * kMaxStages, bar_tempty = bar_tfull + 16u,
@@ -232,6 +234,12 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
   for (int i = threadIdx.x; i < kMaxC; i += blockDim.x) {
     s_scale[i] = i < p.Cout ? p.scale[i] : 0.f;
     s_shift[i] = i < p.Cout ? p.shift[i] : 0.f;
+  }
+  if constexpr (kDw) {     // constants of the layer, like scale / shift: loaded before the dependency wait
+    for (int i = threadIdx.x; i < a.nchunks * 9 * kBK; i += blockDim.x) {
+      const int ch = i & (kBK - 1), t = (i >> 6) % 9, c = i / (9 * kBK);
+      s_dww[i] = (c * kBK + ch < p.Cin) ? a.dw_w[t * p.Cin + c * kBK + ch] : 0.f;
+    }
   }
   // barrier set-up spread over the first threads (one pipeline stage each) instead of ~55 serial inits in thread 0: the
   // prologue is part of the fixed cost every launch pays
@@ -525,29 +533,35 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
       // thread.  Row-accumulate form: halo row j adds into output rows j-2 .. j, so at most three output rows are live.
       const int cp = tg & 31, sub = tg >> 5;
       const int x0 = (sub & 3) * 4, y0 = (sub >> 2) * 4;
-      const uint32_t h_thread = (uint32_t)((y0 * kHaloW + x0) * (kBK * 2) + cp * 4);
-      uint32_t a_off[4];                               // this thread's bytes within an A-stage row, per output column (swizzle by column)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a_off[i] = (uint32_t)((x0 + i) * 128 + ((((cp >> 2) ^ ((x0 + i) & 7)) << 4) + (cp & 3) * 4));
+      // three per-thread constants carry all the addressing (the compiler otherwise re-derived five offsets from threadIdx for
+      // every item): the halo offset, the A-stage offset of output column 0 and the swizzle term -- column i of a row sits at
+      // a_base + 128 i + (kx ^ 16 i), i.e. one LOP3 + one add per column and per item, the row offsets are immediates
+      uint32_t h_off = (uint32_t)((y0 * kHaloW + x0) * (kBK * 2) + cp * 4);
+      uint32_t a_base = (uint32_t)(y0 * kTW * 128 + x0 * 128 + (cp & 3) * 4) | ((uint32_t)(((cp >> 2) ^ (x0 & 4)) << 4) << 20);   // kx in bits 24..26
+      asm volatile("" : "+r"(h_off), "+r"(a_base));       // opaque: keep them in registers instead of re-deriving them from threadIdx per item
+      const uint32_t kx = a_base >> 20;
+      const uint32_t w_off = smem_u32(s_dww) + (uint32_t)cp * 8u;
       float2 w[9];
       for (int it = grp; it < items; it += 2) {
-        if (c != cur_c) {
+        if (c != cur_c) {                              // this chunk's 9 x 2 weights from the [chunk][tap][64] image in shared memory
           cur_c = c;
-          const int ch = c * kBK + cp * 2;
-          const bool ch_ok = ch < p.Cin;
+          const uint32_t wp = w_off + (uint32_t)c * (9u * kBK * 4u);
 #pragma unroll
-          for (int t = 0; t < 9; ++t) w[t] = ch_ok ? __ldg(reinterpret_cast<const float2*>(a.dw_w + t * p.Cin + ch)) : make_float2(0.f, 0.f);
+          for (int t = 0; t < 9; ++t) w[t] = lds_f2(wp + (uint32_t)t * (kBK * 4));
         }
         mbar_wait(bar_hfull + 8u * rh.idx, rh.phase);
         mbar_wait(bar_aempty + 8u * ra.idx, ra.phase ^ 1u);
-        const uint8_t* hb = g_halo + (size_t)rh.idx * kHaloBytes + h_thread;
-        uint8_t* ab = smem + (size_t)ra.idx * kAStageBytes + (size_t)y0 * kTW * 128;
+        const uint32_t hb = sH + (uint32_t)rh.idx * kHaloBytes + h_off;
+        const uint32_t ab0 = sA + (uint32_t)ra.idx * kAStageBytes + (a_base & 0xfffffu);
+        uint32_t ab[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ab[i] = ab0 + (uint32_t)i * 128u + (kx ^ ((uint32_t)i << 4));
         float2 acc[3][4];
 #pragma unroll
         for (int j = 0; j < 6; ++j) {                  // halo rows y0 - 1 + j
           float2 x[6];
 #pragma unroll
-          for (int i = 0; i < 6; ++i) x[i] = Cv<T>::up(*reinterpret_cast<const uint32_t*>(hb + (j * kHaloW + i) * (kBK * 2)));
+          for (int i = 0; i < 6; ++i) x[i] = Cv<T>::up(lds_u32(hb + (uint32_t)((j * kHaloW + i) * (kBK * 2))));
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {             // this halo row is tap row ky of output row j - ky
             const int r = j - ky;
@@ -563,8 +577,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
           if (j >= 2) {                                // output row j - 2 is complete
             const int r = j - 2;
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              *reinterpret_cast<uint32_t*>(ab + r * kTW * 128 + a_off[i]) = Cv<T>::pack(acc[r % 3][i].x, acc[r % 3][i].y);
+            for (int i = 0; i < 4; ++i) sts_u32(ab[i] + (uint32_t)(r * kTW * 128), Cv<T>::pack(acc[r % 3][i].x, acc[r % 3][i].y));
           }
         }
         fence_proxy_async();
@@ -647,7 +660,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
 
 size_t fused_smem_bytes(const FusedArgs& a) {
   return 1024 + (size_t)a.SA * kAStageBytes + (size_t)a.SB * a.b_stage_bytes + (size_t)a.ring * kSlabBytes +
-         (size_t)a.SH * kHaloBytes + 2 * kMaxC * sizeof(float) + (6 * kMaxStages + 4 + kMaxRing) * 8 + 16;
+         (size_t)a.SH * kHaloBytes + 2 * kMaxC * sizeof(float) + (size_t)a.dww_bytes + (6 * kMaxStages + 4 + kMaxRing) * 8 + 16;
 }
 
 template <typename T, bool kDw, bool kRes, bool kPair>
@@ -776,6 +789,7 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
   a.dw_w = dw;
   a.has_res = p.res.ptr ? 1 : 0;
   a.nchunks = (p.Cin + kBK - 1) / kBK;
+  a.dww_bytes = a.dw_mode ? a.nchunks * 9 * kBK * (int)sizeof(float) : 0;
   a.w_kblocks = p.wtaps * a.nchunks;
   if (!pick_tile(p.MH, p.MW, p.N, &a.bw, &a.bh, &a.bn)) return cudaErrorInvalidValue;
   a.a_tile_bytes = a.bw * a.bh * a.bn * 128;
