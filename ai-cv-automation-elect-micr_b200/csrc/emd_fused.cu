@@ -202,13 +202,15 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
   uint8_t* g_halo = smem + (sH - smem_base);
   float* s_scale = reinterpret_cast<float*>(g_halo + (size_t)SH * kHaloBytes);
   float* s_shift = s_scale + kMaxC;
-  float* s_dww = s_shift + kMaxC;              // dw mode: depthwise weights as [chunk][tap][64 channels] (a.dww_bytes; 0 in taps mode)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_dww) + a.dww_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + kMaxC);
   const uint32_t bar_afull = smem_u32(bars), bar_aempty = bar_afull + 8u * kMaxStages, bar_bfull = bar_aempty + 8u * kMaxStages,
                  bar_bempty = bar_bfull + 8u * kMaxStages, bar_hfull = bar_bempty + 8u * kMaxStages,
                  bar_hempty = bar_hfull + 8u * kMaxStages, bar_tfull = bar_hempty + 8u * kMaxStages, bar_tempty = bar_tfull + 16u,
                  bar_rfull = bar_tempty + 16u;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 * kMaxStages + 4 + kMaxRing);
+  // dw mode, where the stage budget leaves room (a.dww_bytes > 0): the depthwise weights as a [chunk][tap][64 channels] image
+  // at the very end of the carve, used by the math warps only
+  float* s_dww = reinterpret_cast<float*>(tmem_slot + 4);
 
   // warp index through a shuffle: the compiler can then prove the role branches warp-uniform and keep the MMA issuer's
   // descriptors in uniform registers (otherwise every tcgen05.mma sits in an ELECT / 7x R2UR waterfall loop)
@@ -235,7 +237,7 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
     s_scale[i] = i < p.Cout ? p.scale[i] : 0.f;
     s_shift[i] = i < p.Cout ? p.shift[i] : 0.f;
   }
-  if constexpr (kDw) {     // constants of the layer, like scale / shift: loaded before the dependency wait
+  if (kDw && a.dww_bytes) {     // constants of the layer, like scale / shift: loaded before the dependency wait
     for (int i = threadIdx.x; i < a.nchunks * 9 * kBK; i += blockDim.x) {
       const int ch = i & (kBK - 1), t = (i >> 6) % 9, c = i / (9 * kBK);
       s_dww[i] = (c * kBK + ch < p.Cin) ? a.dw_w[t * p.Cin + c * kBK + ch] : 0.f;
@@ -543,11 +545,18 @@ fused_conv_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ C
       const uint32_t w_off = smem_u32(s_dww) + (uint32_t)cp * 8u;
       float2 w[9];
       for (int it = grp; it < items; it += 2) {
-        if (c != cur_c) {                              // this chunk's 9 x 2 weights from the [chunk][tap][64] image in shared memory
+        if (c != cur_c) {                              // this chunk's 9 x 2 weights: from the [chunk][tap][64] image in shared memory, or global
           cur_c = c;
-          const uint32_t wp = w_off + (uint32_t)c * (9u * kBK * 4u);
+          if (a.dww_bytes) {
+            const uint32_t wp = w_off + (uint32_t)c * (9u * kBK * 4u);
 #pragma unroll
-          for (int t = 0; t < 9; ++t) w[t] = lds_f2(wp + (uint32_t)t * (kBK * 4));
+            for (int t = 0; t < 9; ++t) w[t] = lds_f2(wp + (uint32_t)t * (kBK * 4));
+          } else {
+            const int ch = c * kBK + cp * 2;
+            const bool ch_ok = ch < p.Cin;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) w[t] = ch_ok ? __ldg(reinterpret_cast<const float2*>(a.dw_w + t * p.Cin + ch)) : make_float2(0.f, 0.f);
+          }
         }
         mbar_wait(bar_hfull + 8u * rh.idx, rh.phase);
         mbar_wait(bar_aempty + 8u * ra.idx, ra.phase ^ 1u);
@@ -789,7 +798,7 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
   a.dw_w = dw;
   a.has_res = p.res.ptr ? 1 : 0;
   a.nchunks = (p.Cin + kBK - 1) / kBK;
-  a.dww_bytes = a.dw_mode ? a.nchunks * 9 * kBK * (int)sizeof(float) : 0;
+  a.dww_bytes = 0;
   a.w_kblocks = p.wtaps * a.nchunks;
   if (!pick_tile(p.MH, p.MW, p.N, &a.bw, &a.bh, &a.bn)) return cudaErrorInvalidValue;
   a.a_tile_bytes = a.bw * a.bh * a.bn * 128;
@@ -824,6 +833,15 @@ static cudaError_t launch_impl(const ConvParams* ps, int nvar, int et, const flo
       if (a.SA > 2) { --a.SA; continue; }
       if (a.ring == 3) { a.ring = 2; continue; }
       return cudaErrorInvalidValue;
+    }
+    // the depthwise-weight image in shared memory only where it costs no pipeline stage (layers with several chunks per group
+    // switch chunks every item: 9 LDS.64 with immediate offsets instead of 9 global loads and their pointer arithmetic)
+    // (measured, deconv1_0, 384 -> 128: a third weight stage given up for the image is a gain, 0.66 -> 0.60 ms; a halo stage is
+    // a loss, deconv1_1 0.30 -> 0.40 ms)
+    a.dww_bytes = (a.dw_cols && a.nchunks > 2) ? a.nchunks * 9 * kBK * (int)sizeof(float) : 0;
+    if (a.dww_bytes && fused_smem_bytes(a) > (size_t)kSmemLimit) {
+      if (a.SB > 2) { --a.SB; if (fused_smem_bytes(a) > (size_t)kSmemLimit) { ++a.SB; a.dww_bytes = 0; } }
+      else a.dww_bytes = 0;
     }
   } else {
     a.pair = want_pair(a.m_tiles, a.nt, nvar, num_sms) ? 1 : 0;
