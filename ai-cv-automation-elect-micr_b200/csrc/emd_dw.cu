@@ -16,7 +16,7 @@ namespace {
 constexpr int kTH = 8, kTW = 16, kHaloH = kTH + 2, kHaloW = kTW + 2;
 constexpr int kChunk = 64;
 constexpr int kStageBytes = kHaloH * kHaloW * kChunk * 2;  // 23040
-constexpr int kStages = 4;
+constexpr int kMaxStages = 8;     // stage count is a launch argument (even, 4..8): two groups own the stages of their parity
 constexpr int kGroupWarps = 8;
 constexpr int kMathThreads = 2 * kGroupWarps * 32;   // two groups of 8 warps take alternate items
 
@@ -28,6 +28,7 @@ struct DwTmaArgs {
   // summed over channels, then scale/shift, ReLU6, clip and an FP32 store
   float scale, shift;
   int relu6, clip01;
+  int stages;   // depth of the halo ring (even)
   int cols;     // thread mapping: 1 = 2 channels x 4 columns x 4 rows (conflict-free 128-byte LDS, 40 % fewer unpacks), 0 = 4 channels x 1 column x 8 rows
 };
 
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(kMathThreads + 32, 1) dw_tma_kernel(const __gr
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 127u) & ~127u;
   uint8_t* smem = smem_raw + (base - raw);
+  const int kStages = a.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   const uint32_t bar_full = ptx::smem_u32(bars), bar_empty = bar_full + 8u * kStages;
   const DwParams& p = a.p;
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(kMathThreads + 32, 1) dw_tma_kernel(const __gr
           const int n_img = tile / a.tiles_per_img;
           const int rem = tile - n_img * a.tiles_per_img;
           const int by = rem / a.tiles_x, bx = rem - by * a.tiles_x;
-          const int q = g + 2 * k, s = q % kStages;          // group g owns the stages of its own parity (kStages is even)
+          const int q = g + 2 * k, s = q % kStages;          // group g owns the stages of its own parity (the stage count is even)
           const uint32_t ph = (uint32_t)((q / kStages) & 1);
           ptx::mbar_wait(bar_empty + 8u * s, ph ^ 1u);
           ptx::mbar_arrive_expect_tx(bar_full + 8u * s, kStageBytes);
@@ -369,7 +371,10 @@ static cudaError_t launch_common(DwTmaArgs& a, int et, bool reduce, int num_sms,
   void* base = reinterpret_cast<char*>(p.in.ptr) + (size_t)p.in.coff * 2;
   if (!tma_encode_nhwc(&tmap, et == ET_BF16, base, p.in.C, p.in.W, p.in.H, p.N, p.in.pitch, kChunk, kHaloW, kHaloH, 1, false))
     return cudaErrorInvalidValue;
-  const size_t smem = 128 + (size_t)kStages * kStageBytes + 2 * kStages * 8;
+  int st = tuning().dw_stages ? tuning().dw_stages : 4;
+  st = st < 2 ? 2 : st > kMaxStages ? kMaxStages : st & ~1;
+  a.stages = st;
+  const size_t smem = 128 + (size_t)kMaxStages * kStageBytes + 2 * kMaxStages * 8;   // attribute set once for the deepest ring
   const int grid = a.items < num_sms ? a.items : num_sms;
   if (et == ET_BF16)
     return reduce ? launch_t<__nv_bfloat16, true>(a, tmap, grid, smem, s) : launch_t<__nv_bfloat16, false>(a, tmap, grid, smem, s);

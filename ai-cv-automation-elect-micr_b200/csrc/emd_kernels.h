@@ -158,6 +158,7 @@ struct Tuning {
   int pair_min_rows = 128; // EMD_PAIR_MIN_ROWS: CTA pairs only for N tiles of at least this many columns
   int pair_min_items = -1; // EMD_PAIR_MIN_ITEMS: CTA pairs only from this many pair items on (-1 = the number of SMs)
   int io_slices = 0, io_parts = 0;              // EMD_IO_SLICES, EMD_IO_PARTS (0 = defaults)
+  int dw_stages = 0;       // EMD_DW_STAGES: halo ring depth of the stand-alone depthwise kernel (even, 2..8; 0 = default 4)
   int dw_sa = 0, dw_sb = 0, dw_sh = 0, dw_ring = 0;   // EMD_DW_SA/SB/SH/RING: stage counts of the fused depthwise mode (0 = defaults)
 };
 Tuning& tuning();

@@ -30,6 +30,7 @@ const Entry kTable[] = {
     {"pair_min_items", "EMD_PAIR_MIN_ITEMS", &Tuning::pair_min_items, false},
     {"io_slices", "EMD_IO_SLICES", &Tuning::io_slices, false},
     {"io_parts", "EMD_IO_PARTS", &Tuning::io_parts, false},
+    {"dw_stages", "EMD_DW_STAGES", &Tuning::dw_stages, false},
     {"dw_sa", "EMD_DW_SA", &Tuning::dw_sa, false},
     {"dw_sb", "EMD_DW_SB", &Tuning::dw_sb, false},
     {"dw_sh", "EMD_DW_SH", &Tuning::dw_sh, false},
