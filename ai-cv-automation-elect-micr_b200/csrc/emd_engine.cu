@@ -27,6 +27,7 @@ thread_local std::string g_create_error;
 struct Tensor {
   std::string name;
   int H, W, C;
+  int pitch = 0;        // elements per pixel as laid out in the arena (>= C: odd channel counts are padded to whole 128-byte lines)
   bool external;        // network input / output: lives in caller (or staging) memory, always f32
   size_t offset = 0;    // bytes into the arena (image 0 of the batch)
   size_t bytes = 0;     // bytes reserved (max_batch images, 4-byte elements)
@@ -166,7 +167,7 @@ bool is_device_ptr(const void* p) {
 struct Builder {
   emd_engine* e;
   int add_tensor(const std::string& name, int H, int W, int C, bool external = false) {
-    Tensor t; t.name = name; t.H = H; t.W = W; t.C = C; t.external = external;
+    Tensor t; t.name = name; t.H = H; t.W = W; t.C = C; t.pitch = C; t.external = external;
     e->tensors.push_back(t);
     int id = (int)e->tensors.size() - 1;
     e->named[name] = Ref{id, 0, C};
@@ -385,7 +386,18 @@ int plan_arena(emd_engine* e) {
   for (int i = 0; i < (int)e->tensors.size(); ++i) {
     Tensor& t = e->tensors[i];
     if (t.external || t.last < 0) continue;
-    t.bytes = (((size_t)t.H * t.W * t.C * 4 * e->max_batch) + 1023) & ~(size_t)1023;
+    // A pixel of a 728-channel tensor is 1456 bytes: every 64-channel chunk of it (the 128-byte row of a TMA box, a warp's
+    // 128-byte load or store) straddles two 128-byte lines and starts on a half sector for odd pixels.  Laid out with a pitch of
+    // 768 channels every chunk is one aligned line; the 40 padding channels are never read or written (the tensor maps and the
+    // kernels see C = 728).  Only for tensors that are never addressed as channel slices (concat buffers keep their layout).
+    if (tuning().pad_pitch && t.C > 64 && (t.C & 63)) {
+      bool sliced = false;
+      for (const Step& st : e->steps)
+        for (const Ref* r : {&st.in, &st.out, &st.res})
+          if (r->t == i && (r->coff != 0 || r->C != t.C)) sliced = true;
+      if (!sliced) t.pitch = (t.C + 63) & ~63;
+    }
+    t.bytes = (((size_t)t.H * t.W * t.pitch * 4 * e->max_batch) + 1023) & ~(size_t)1023;
     if (e->keep) { t.first = 0; t.last = 1 << 30; }
     order.push_back(i);
   }
@@ -520,12 +532,12 @@ View make_view(const ExecCtx& c, Ref r) {
   View v; v.H = t.H; v.W = t.W; v.C = r.C;
   for (const Override& o : c.ov)
     if (o.t == r.t) { v.ptr = o.ptr; v.pitch = r.C; v.coff = 0; return v; }
-  v.pitch = t.C; v.coff = r.coff;
+  v.pitch = t.pitch; v.coff = r.coff;
   size_t esz = 4;     // network input and output are FP32 images
   if (r.t == c.e->t_input) v.ptr = const_cast<float*>(c.d_in);
   else if (r.t == c.e->t_output) v.ptr = c.d_out;
   else { v.ptr = c.e->arena + t.offset; esz = c.et == ET_F32 ? 4 : 2; }
-  if (c.b0) v.ptr = reinterpret_cast<char*>(v.ptr) + (size_t)c.b0 * t.H * t.W * t.C * esz;
+  if (c.b0) v.ptr = reinterpret_cast<char*>(v.ptr) + (size_t)c.b0 * t.H * t.W * t.pitch * esz;
   return v;
 }
 
@@ -627,8 +639,10 @@ cudaError_t run_step_impl(ExecCtx& c, int idx) {
       p.pad = (s.stride == 1) ? s.rate : 0;  // TF SAME: symmetric `rate` at stride 1; 0 before / 1 after at stride 2 on even sizes
       p.w = s.dw; p.in_f32 = ti.external;
       e->cnt.launches++;
+      if (tuning().dw_reg_all && dw_reg_supported(p, c.et)) return launch_dw_reg(p, c.et, c.s);
       if (e->use_umma && dw_tma_supported(p, c.et)) return launch_dw_tma(p, c.et, e->num_sms, c.s);
       if (e->use_umma && dw_s2_tma_supported(p, c.et)) return launch_dw_s2_tma(p, c.et, e->num_sms, c.s);
+      if (tuning().dw_reg && dw_reg_supported(p, c.et)) return launch_dw_reg(p, c.et, c.s);
       if (tuning().dw_tile && dw_tile_supported(p, c.et)) return launch_dw_tile(p, c.et, c.s);
       if (tuning().dw_strip && dw_strip_supported(p, c.et)) return launch_dw_strip(p, c.et, c.s);
       return launch_dw3x3(p, c.et, c.s);
@@ -1506,7 +1520,7 @@ int emd_get_activation(emd_engine* e, const char* name, float* out, size_t cap_e
   if (!out) return EMD_OK;  // size query
   if (cap_elems < need) return fail(e, EMD_EINVAL, "buffer holds %zu elements, %zu needed", cap_elems, need);
   CU(e, cudaSetDevice(e->device));
-  View v; v.ptr = e->arena + t.offset; v.H = t.H; v.W = t.W; v.pitch = t.C; v.coff = r.coff; v.C = r.C;
+  View v; v.ptr = e->arena + t.offset; v.H = t.H; v.W = t.W; v.pitch = t.pitch; v.coff = r.coff; v.C = r.C;
   return download_view(e, v, e->last_n, e->last_et, false, out, e->stream);
 }
 

@@ -82,6 +82,8 @@ bool dw_strip_supported(const DwParams& p, int et);   // 16-bit, stride 1: warp 
 cudaError_t launch_dw_strip(const DwParams& p, int et, cudaStream_t s);
 bool dw_tile_supported(const DwParams& p, int et);    // 16-bit, stride 1, rate 1: warp = 8 x 8 pixel tile x 64 channels, halo staged in smem by cp.async
 cudaError_t launch_dw_tile(const DwParams& p, int et, cudaStream_t s);
+bool dw_reg_supported(const DwParams& p, int et);    // register-strip form (emd_kernels_simt.cu): stride 1, rate 1, any map size
+cudaError_t launch_dw_reg(const DwParams& p, int et, cudaStream_t s);
 cudaError_t launch_resize(const ResizeParams& p, int et, cudaStream_t s);
 cudaError_t launch_avgpool(const PoolParams& p, int et, cudaStream_t s);
 cudaError_t launch_stem(const StemParams& p, int et, cudaStream_t s);
@@ -151,8 +153,11 @@ struct Tuning {
   int mid_graph = 1;       // EMD_DISABLE_MID_GRAPH: no graph replay of the whole-batch middle section
   int skip_taps = 1;       // EMD_DISABLE_SKIP_TAPS: dilated / transposed convs multiply every tap on every tile, padding or not
   int dw_tile = 1;         // EMD_DISABLE_DW_TILE: small-map depthwise on the strip kernel (no shared-memory staging)
+  int dw_reg = 1;          // EMD_DISABLE_DW_REG: small-map depthwise on the shared-memory tile kernel instead of the register-strip kernel
+  int dw_reg_all = 0;      // EMD_DW_REG_ALL=1: the register-strip kernel also where the TMA-fed depthwise kernel applies (A/B)
   int dw_strip = 1;        // EMD_DISABLE_DW_STRIP: small-map / dilated depthwise on the one-thread-per-pixel kernel
   int dw_cols = 1;         // EMD_DISABLE_DW_COLS: depthwise producer with one pixel column per thread (first form)
+  int pad_pitch = 1;       // EMD_DISABLE_PAD_PITCH: 728-channel tensors dense (1456-byte pixels) instead of padded to 768 channels (read at emd_create)
   int strict = 0;          // EMD_STRICT=1: a GEMM-class layer of a 16-bit mode that would run on the CUDA-core kernel is an error
   int graph_max_n = 32;    // EMD_GRAPH_MAX_N: largest batch replayed from a graph
   int pair_min_rows = 128; // EMD_PAIR_MIN_ROWS: CTA pairs only for N tiles of at least this many columns

@@ -508,6 +508,103 @@ cudaError_t launch_dw_tile(const DwParams& p, int et, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+// Register form for the same small maps (and any stride-1, rate-1 map): a warp = the 32 channel pairs of a strip of kCW output columns of
+// one image, walked down a block of up to kRegRows rows.  Nothing is staged: each halo row is kCW + 2 predicated LDG.32 (one 128-byte line
+// per instruction, kAhead rows = 24-32 lines in flight per warp), lives in registers, and feeds the three output rows it touches.  Against
+// the shared-memory tile kernel above there is no load-then-wait phase per warp, no 8 x 8 tile to waste on a 6 x 6 map (one strip is the
+// whole map) and a third of the instructions.  Same tap order as the other depthwise kernels: bit-identical results.
+constexpr int kRegRows = 12;
+template <typename T, int kCW, int kAhead>
+__global__ void __launch_bounds__(128) dw_reg_kernel(const DwParams p, int nchunks, int strips, int row_blocks, long long n_items) {
+  constexpr int kLW = kCW + 2;
+  const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (item >= n_items) return;
+  const int lane = threadIdx.x & 31;
+  long long q = item;
+  const int c = (int)(q % nchunks); q /= nchunks;
+  const int st = (int)(q % strips); q /= strips;
+  const int rb = (int)(q % row_blocks);
+  const int n = (int)(q / row_blocks);
+  const int cw = c * 32 + lane;                              // channel pair
+  if (2 * cw >= p.in.C) return;
+  const int H = p.in.H, W = p.in.W;
+  const int x0 = st * kCW, y0 = rb * kRegRows;
+  const int rows = min(kRegRows, H - y0);
+  const uint32_t* gin = reinterpret_cast<const uint32_t*>(reinterpret_cast<const T*>(p.in.ptr) + p.in.coff);
+  uint32_t* gout = reinterpret_cast<uint32_t*>(reinterpret_cast<T*>(p.out.ptr) + p.out.coff);
+  const int ipitch = p.in.pitch >> 1, opitch = p.out.pitch >> 1;
+  float2 w[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) w[t] = __ldg(reinterpret_cast<const float2*>(p.w + t * p.in.C + 2 * cw));
+  uint32_t x_ok = 0;                                         // bit i: halo column x0 - 1 + i is inside the image
+#pragma unroll
+  for (int i = 0; i < kLW; ++i) x_ok |= (uint32_t)(x0 - 1 + i >= 0 && x0 - 1 + i < W) << i;
+  const int ncol = min(kCW, W - x0);
+  const long long irs = (long long)W * ipitch, ors = (long long)p.OW * opitch;
+  // running pointers: halo row 0 = image row y0 - 1, halo column 0 = image column x0 - 1 (never dereferenced outside the image)
+  const uint32_t* pin = gin + (((long long)n * H + (y0 - 1)) * W + (x0 - 1)) * ipitch + cw;
+  uint32_t* pout = gout + (((long long)n * p.OH + y0) * p.OW + x0) * opitch + cw;
+  uint32_t raw[kAhead][kLW];
+  int yl = y0 - 1;
+  auto load_row = [&](int slot) {
+    const uint32_t m = (yl >= 0 && yl < H) ? x_ok : 0u;
+#pragma unroll
+    for (int i = 0; i < kLW; ++i) raw[slot][i] = ((m >> i) & 1u) ? __ldg(pin + (long long)i * ipitch) : 0u;
+    pin += irs;
+    ++yl;
+  };
+#pragma unroll
+  for (int j = 0; j < kAhead; ++j)
+    if (j < rows + 2) load_row(j);
+  float2 acc[3][kCW];
+#pragma unroll
+  for (int j = 0; j < kRegRows + 2; ++j) {
+    if (j >= rows + 2) break;
+    float2 x[kLW];
+#pragma unroll
+    for (int i = 0; i < kLW; ++i) x[i] = unpack2<T>(raw[j % kAhead][i]);
+    if (j + kAhead < rows + 2) load_row(j % kAhead);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int r = j - ky;
+      if (r < 0 || r >= kRegRows) continue;
+#pragma unroll
+      for (int i = 0; i < kCW; ++i) {
+        float2& d = acc[r % 3][i];
+        d = ky == 0 ? ptx::fmul2(x[i], w[0]) : ptx::ffma2(x[i], w[ky * 3], d);
+        d = ptx::ffma2(x[i + 1], w[ky * 3 + 1], d);
+        d = ptx::ffma2(x[i + 2], w[ky * 3 + 2], d);
+      }
+    }
+    if (j >= 2) {
+#pragma unroll
+      for (int i = 0; i < kCW; ++i)
+        if (i < ncol) pout[(long long)i * opitch] = pack2<T>(acc[(j - 2) % 3][i].x, acc[(j - 2) % 3][i].y);
+      pout += ors;
+    }
+  }
+}
+
+bool dw_reg_supported(const DwParams& p, int et) {
+  return dw_strip_supported(p, et) && p.rate == 1;
+}
+
+cudaError_t launch_dw_reg(const DwParams& p, int et, cudaStream_t s) {
+  const int nchunks = (p.in.C + 63) / 64, row_blocks = (p.OH + kRegRows - 1) / kRegRows;
+  const bool wide = (p.OW % 8 == 0) && (p.OW % 6 != 0);      // 8-column strips where they tile the row and 6-column ones do not
+  const int cw = wide ? 8 : 6, strips = (p.OW + cw - 1) / cw;
+  const long long n_items = (long long)p.N * row_blocks * strips * nchunks;
+  const unsigned blocks = (unsigned)((n_items + 3) / 4);
+  if (et == ET_BF16) {
+    if (wide) dw_reg_kernel<__nv_bfloat16, 8, 3><<<blocks, 128, 0, s>>>(p, nchunks, strips, row_blocks, n_items);
+    else dw_reg_kernel<__nv_bfloat16, 6, 4><<<blocks, 128, 0, s>>>(p, nchunks, strips, row_blocks, n_items);
+  } else {
+    if (wide) dw_reg_kernel<__half, 8, 3><<<blocks, 128, 0, s>>>(p, nchunks, strips, row_blocks, n_items);
+    else dw_reg_kernel<__half, 6, 4><<<blocks, 128, 0, s>>>(p, nchunks, strips, row_blocks, n_items);
+  }
+  return cudaGetLastError();
+}
+
 template <typename TI, typename TO>
 static cudaError_t launch_dw_t(const DwParams& p, cudaStream_t s) {
   const int C = p.in.C;
@@ -539,12 +636,13 @@ cudaError_t launch_dw3x3(const DwParams& p, int et, cudaStream_t s) {
 // optional per-channel affine + ReLU6 (the BN/ReLU6 that follows the image-level branch, DMG:345)
 // ---------------------------------------------------------------------------------------------
 template <typename T, int V>
-__global__ void __launch_bounds__(256) resize_kernel(const ResizeParams p, int fx) {
-  // thread = (fx consecutive output pixels of one row, V channels); blockIdx.y = output row, blockIdx.z = image.
+__global__ void __launch_bounds__(256) resize_kernel(const ResizeParams p, int fx, int fy) {
+  // thread = (fx consecutive output pixels of fy consecutive rows, V channels); blockIdx.y = output row group, blockIdx.z = image.
+  // fy = out.H / in.H when that is a power of two (the x4 decoder upsample: the 16 outputs of a source cell come from four loads).
   // fx = out.W / in.W when that is an integer (x4 decoder upsample, x2 image-level branch, x1 BN-only steps): the fx
   // outputs share their two source columns, so each source vector is fetched once per thread instead of once per output.
   const int C = p.in.C, cg = C / V;
-  const int oy = blockIdx.y, n = blockIdx.z;
+  const int oy = blockIdx.y * fy, n = blockIdx.z;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int strips = p.out.W / fx;
   if (idx >= strips * cg) return;
@@ -553,7 +651,6 @@ __global__ void __launch_bounds__(256) resize_kernel(const ResizeParams p, int f
   const float sy = oy * ry;
   const int y0 = (int)floorf(sy);
   const int y1 = min(y0 + 1, p.in.H - 1);
-  const float wy = sy - y0;
   const int ox0 = sx_i * fx;
   const int x0 = (int)floorf(ox0 * rx);
   const int x1 = min(x0 + 1, p.in.W - 1);
@@ -568,20 +665,23 @@ __global__ void __launch_bounds__(256) resize_kernel(const ResizeParams p, int f
     for (int j = 0; j < V; ++j) { sc[j] = p.scale[g * V + j]; sh[j] = p.shift[g * V + j]; }
   }
   T* op = reinterpret_cast<T*>(p.out.ptr) + (((size_t)n * p.out.H + oy) * p.out.W + ox0) * p.out.pitch + p.out.coff + g * V;
-  for (int r = 0; r < fx; ++r) {
-    const float sx = (ox0 + r) * rx;
-    const float wx = sx - (float)x0;     // same x0 for the whole strip (fx divides the scale)
-    float o[V];
+  for (int q = 0; q < fy; ++q) {
+    const float wy = (oy + q) * ry - (float)y0;   // same y0 for the whole row group (fy is a power of two: the products are exact)
+    for (int r = 0; r < fx; ++r) {
+      const float sx = (ox0 + r) * rx;
+      const float wx = sx - (float)x0;     // same x0 for the whole strip (fx divides the scale)
+      float o[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      const float top = tl[j] + (tr[j] - tl[j]) * wx;
-      const float bot = bl[j] + (br[j] - bl[j]) * wx;
-      float v = top + (bot - top) * wy;
-      if (p.scale) v = fmaf(v, sc[j], sh[j]);
-      if (p.relu6) v = fminf(fmaxf(v, 0.f), 6.f);
-      o[j] = v;
+      for (int j = 0; j < V; ++j) {
+        const float top = tl[j] + (tr[j] - tl[j]) * wx;
+        const float bot = bl[j] + (br[j] - bl[j]) * wx;
+        float v = top + (bot - top) * wy;
+        if (p.scale) v = fmaf(v, sc[j], sh[j]);
+        if (p.relu6) v = fminf(fmaxf(v, 0.f), 6.f);
+        o[j] = v;
+      }
+      VecIO<T, V>::st(op + ((size_t)q * p.out.W + r) * p.out.pitch, o);
     }
-    VecIO<T, V>::st(op + (size_t)r * p.out.pitch, o);
   }
 }
 
@@ -593,12 +693,14 @@ static cudaError_t launch_resize_t(const ResizeParams& p, cudaStream_t s) {
   (void)px;
   if (p.N > 65535 || p.out.H > 65535) return cudaErrorInvalidValue;
   const int fx = (p.out.W % p.in.W == 0 && p.out.W / p.in.W <= 8) ? p.out.W / p.in.W : 1;
+  const int ry = p.out.H % p.in.H == 0 ? p.out.H / p.in.H : 1;
+  const int fy = (ry == 2 || ry == 4 || ry == 8) ? ry : 1;
   if (sizeof(T) == 2 && al8) {
-    dim3 grid((unsigned)(((p.out.W / fx) * (C / 8) + 255) / 256), (unsigned)p.out.H, (unsigned)p.N);
-    resize_kernel<T, 8><<<grid, 256, 0, s>>>(p, fx);
+    dim3 grid((unsigned)(((p.out.W / fx) * (C / 8) + 255) / 256), (unsigned)(p.out.H / fy), (unsigned)p.N);
+    resize_kernel<T, 8><<<grid, 256, 0, s>>>(p, fx, fy);
   } else {
-    dim3 grid((unsigned)(((p.out.W / fx) * (C / 4) + 255) / 256), (unsigned)p.out.H, (unsigned)p.N);
-    resize_kernel<T, 4><<<grid, 256, 0, s>>>(p, fx);
+    dim3 grid((unsigned)(((p.out.W / fx) * (C / 4) + 255) / 256), (unsigned)(p.out.H / fy), (unsigned)p.N);
+    resize_kernel<T, 4><<<grid, 256, 0, s>>>(p, fx, fy);
   }
   return cudaGetLastError();
 }
@@ -661,64 +763,77 @@ cudaError_t launch_avgpool(const PoolParams& p, int et, cudaStream_t s) {
 // Two phases per block of 256 consecutive output pixels: (1) one thread per pixel computes d once into shared
 // memory; (2) the block streams the pixels x channels out as consecutive 16-byte chunks (a warp instruction
 // writes 512 contiguous bytes), each thread keeping the weights / scale / shift of its fixed 8-channel group.
+constexpr int kStemGroups = 4;   // 256-pixel groups per block: the 24 per-thread constants are loaded once per 1024 pixels
 template <typename T>
 __global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
-  __shared__ float s_d[256];
+  __shared__ float s_d[2][256];
   const int OW = p.out.W, OH = p.out.H;
   const long long npix = (long long)p.N * OH * OW;
-  const long long pix0 = (long long)blockIdx.x * 256;
-  {
-    const long long pix = pix0 + threadIdx.x;
-    float d = 0.f;
-    if (pix < npix) {
-      // 32-bit index arithmetic (the launcher guarantees npix < 2^31): three 64-bit divisions per thread were a visible part of
-      // this write-bound kernel's instruction stream
-      const unsigned upix = (unsigned)pix;
-      const int ox = (int)(upix % (unsigned)OW);
-      const unsigned r = upix / (unsigned)OW;
-      const int oy = (int)(r % (unsigned)OH), n = (int)(r / (unsigned)OH);
-      const float* img = p.in + (size_t)n * p.IH * p.IW;
-      if (p.dw) {
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const int iy = oy - 1 + ky;
-          if (iy < 0 || iy >= p.IH) continue;
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const int ix = ox - 1 + kx;
-            if (ix < 0 || ix >= p.IW) continue;
-            d = fmaf(__ldg(img + (size_t)iy * p.IW + ix), p.dw[ky * 3 + kx], d);
-          }
-        }
-      } else {
-        d = __ldg(img + (size_t)(oy * p.istride) * p.IW + ox * p.istride);
-      }
-      if (sizeof(T) == 2) d = to_f(from_f<T>(d));  // the GEMM A operand is 16-bit in the 16-bit modes
-    }
-    s_d[threadIdx.x] = d;
-  }
-  __syncthreads();
   const int cg = p.out.C >> 3;                 // 8-channel groups per pixel (power of two: 8 or 16)
   const int g = threadIdx.x & (cg - 1);
-  float w[8], sc[8], sh[8];
-  VecIO<float, 8>::ld(p.w + g * 8, w);
-  VecIO<float, 8>::ld(p.scale + g * 8, sc);
-  VecIO<float, 8>::ld(p.shift + g * 8, sh);
+  float ws[8], sh[8];                          // weight x folded BN scale, shift: one FFMA per output
+  {
+    float w[8], sc[8];
+    VecIO<float, 8>::ld(p.w + g * 8, w);
+    VecIO<float, 8>::ld(p.scale + g * 8, sc);
+    VecIO<float, 8>::ld(p.shift + g * 8, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ws[j] = w[j] * sc[j];
+  }
+  float dwt[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) dwt[t] = p.dw ? p.dw[t] : 0.f;
   const int ppi = 256 / cg;                    // pixels covered by one pass of the block
   T* obase = reinterpret_cast<T*>(p.out.ptr);
-  for (int k = 0; k < cg; ++k) {
-    const int lp = k * ppi + (threadIdx.x / cg);
-    const long long pix = pix0 + lp;
-    if (pix >= npix) break;
-    const float d = s_d[lp];
-    float o[8];
+  for (int grp = 0; grp < kStemGroups; ++grp) {
+    const long long pix0 = ((long long)blockIdx.x * kStemGroups + grp) * 256;
+    if (pix0 >= npix) break;
+    float* sd = s_d[grp & 1];
+    {
+      const long long pix = pix0 + threadIdx.x;
+      float d = 0.f;
+      if (pix < npix) {
+        // 32-bit index arithmetic (the launcher guarantees npix < 2^31): three 64-bit divisions per thread were a visible part of
+        // this write-bound kernel's instruction stream
+        const unsigned upix = (unsigned)pix;
+        const int ox = (int)(upix % (unsigned)OW);
+        const unsigned r = upix / (unsigned)OW;
+        const int oy = (int)(r % (unsigned)OH), n = (int)(r / (unsigned)OH);
+        const float* img = p.in + (size_t)n * p.IH * p.IW;
+        if (p.dw) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = fmaf(w[j] * d, sc[j], sh[j]);
-      if (p.relu6) v = fminf(fmaxf(v, 0.f), 6.f);
-      o[j] = v;
+          for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oy - 1 + ky;
+            if (iy < 0 || iy >= p.IH) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int ix = ox - 1 + kx;
+              if (ix < 0 || ix >= p.IW) continue;
+              d = fmaf(__ldg(img + (size_t)iy * p.IW + ix), dwt[ky * 3 + kx], d);
+            }
+          }
+        } else {
+          d = __ldg(img + (size_t)(oy * p.istride) * p.IW + ox * p.istride);
+        }
+        if (sizeof(T) == 2) d = to_f(from_f<T>(d));  // the GEMM A operand is 16-bit in the 16-bit modes
+      }
+      sd[threadIdx.x] = d;
     }
-    VecIO<T, 8>::st(obase + (size_t)pix * p.out.pitch + p.out.coff + g * 8, o);
+    __syncthreads();                           // two buffers: the next group's phase 1 cannot overtake this group's readers by more than one sync
+    for (int k = 0; k < cg; ++k) {
+      const int lp = k * ppi + (threadIdx.x / cg);
+      const long long pix = pix0 + lp;
+      if (pix >= npix) break;
+      const float d = sd[lp];
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = fmaf(d, ws[j], sh[j]);
+        if (p.relu6) v = fminf(fmaxf(v, 0.f), 6.f);
+        o[j] = v;
+      }
+      VecIO<T, 8>::st(obase + (size_t)pix * p.out.pitch + p.out.coff + g * 8, o);
+    }
   }
 }
 
@@ -726,7 +841,7 @@ cudaError_t launch_stem(const StemParams& p, int et, cudaStream_t s) {
   const long long npix = (long long)p.N * p.out.H * p.out.W;
   const int cg = p.out.C >> 3;
   if (cg < 1 || cg > 256 || (cg & (cg - 1)) || npix >= (1ll << 31)) return cudaErrorInvalidValue;
-  const unsigned grid = (unsigned)((npix + 255) / 256);
+  const unsigned grid = (unsigned)((npix + 256 * kStemGroups - 1) / (256 * kStemGroups));
   if (et == ET_F32) stem_kernel<float><<<grid, 256, 0, s>>>(p);
   else if (et == ET_BF16) stem_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p);
   else stem_kernel<__half><<<grid, 256, 0, s>>>(p);

@@ -22,8 +22,11 @@ const Entry kTable[] = {
     {"mid_graph", "EMD_DISABLE_MID_GRAPH", &Tuning::mid_graph, true},
     {"skip_taps", "EMD_DISABLE_SKIP_TAPS", &Tuning::skip_taps, true},
     {"dw_tile", "EMD_DISABLE_DW_TILE", &Tuning::dw_tile, true},
+    {"dw_reg", "EMD_DISABLE_DW_REG", &Tuning::dw_reg, true},
+    {"dw_reg_all", "EMD_DW_REG_ALL", &Tuning::dw_reg_all, false},
     {"dw_strip", "EMD_DISABLE_DW_STRIP", &Tuning::dw_strip, true},
     {"dw_cols", "EMD_DISABLE_DW_COLS", &Tuning::dw_cols, true},
+    {"pad_pitch", "EMD_DISABLE_PAD_PITCH", &Tuning::pad_pitch, true},
     {"strict", "EMD_STRICT", &Tuning::strict, false},
     {"graph_max_n", "EMD_GRAPH_MAX_N", &Tuning::graph_max_n, false},
     {"pair_min_rows", "EMD_PAIR_MIN_ROWS", &Tuning::pair_min_rows, false},

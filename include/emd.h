@@ -150,7 +150,7 @@ long long emd_tensor_core_launches(const emd_engine* e);
 long long emd_counter(const emd_engine* e, const char* name);
 /* Tuning / A-B switches (csrc/emd_kernels.h, struct Tuning): process-wide, initialised once from the EMD_* environment, changed
  * by name here; `e` (may be NULL) drops its captured graphs so the change takes effect.  Names: umma, fused, tma, pair,
- * final_umma, pdl, graphs, sliced_io, halves, mid_graph, dw_cols, dw_tile, dw_strip, skip_taps, strict, graph_max_n, pair_min_rows, pair_min_items,
+ * final_umma, pdl, graphs, sliced_io, halves, mid_graph, pad_pitch, dw_cols, dw_reg, dw_reg_all, dw_tile, dw_strip, skip_taps, strict, graph_max_n, pair_min_rows, pair_min_items,
  * io_slices, io_parts, dw_stages, dw_sa, dw_sb, dw_sh, dw_ring.  strict = 1: a GEMM-class layer of a 16-bit mode that no tensor-core
  * kernel supports is an error (EMD_ESTATE) instead of a silent CUDA-core launch. */
 int       emd_set_option(emd_engine* e, const char* name, long long value);
