@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kMathThreads + 32, 1) dw_tma_kernel(const __gr
     for (int t = 0; t < 9; ++t) w[t] = (ch_ok && cnt > 0) ? __ldg(reinterpret_cast<const float2*>(p.w + t * p.in.C + ch)) : make_float2(0.f, 0.f);
     int s = grp % kStages;
     uint32_t ph = (uint32_t)((grp / kStages) & 1);
-    const size_t ostep = (size_t)p.out.W * p.out.pitch;
+    const uint32_t ostep = (uint32_t)p.out.W * (uint32_t)p.out.pitch, opitch = (uint32_t)p.out.pitch;   // element offsets inside a tile fit 32 bits: one IMAD.WIDE.U32 per store address
     for (int k = 0; k < cnt; ++k) {
       const int tile = j0 + k * wc;
       const int n_img = (int)fdiv((uint32_t)tile, a.d_tpi);
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kMathThreads + 32, 1) dw_tma_kernel(const __gr
           const int r = j - 2;
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<uint32_t*>(orow + r * ostep + (size_t)i * p.out.pitch) = Up<T>::pack(acc[r % 3][i].x, acc[r % 3][i].y);
+            *reinterpret_cast<uint32_t*>(orow + ((uint32_t)r * ostep + (uint32_t)i * opitch)) = Up<T>::pack(acc[r % 3][i].x, acc[r % 3][i].y);
         }
       }
       __syncwarp();

@@ -427,6 +427,13 @@ int plan_arena(emd_engine* e) {
     cudaError_t r = cudaMalloc(&e->arena, total);
     if (r != cudaSuccess) return fail(e, EMD_ENOMEM, "workspace of %.2f GB: %s", total / 1e9, cudaGetErrorString(r));
     e->arena_bytes = total;
+    // Every page of a fresh workspace is written once before a kernel sees it.  Measured (tools/keep_repro.py): the FIRST pass
+    // over a newly allocated workspace of >= 28 GB, whose first accesses are TMA loads / stores, intermittently (1 pass in 4)
+    // ended in "unspecified launch failure" or returned a few wrong tiles; later passes over the same memory never did, 21 GB
+    // never did, the CUDA-core kernels never did, and clearing the allocation first removed it (0 of 20).
+    r = cudaMemset(e->arena, 0, total);
+    if (r == cudaSuccess) r = cudaDeviceSynchronize();
+    if (r != cudaSuccess) return fail(e, EMD_ECUDA, "clearing the workspace: %s", cudaGetErrorString(r));
   }
   return EMD_OK;
 }
@@ -729,7 +736,16 @@ cudaError_t run_step_impl(ExecCtx& c, int idx) {
   return cudaErrorInvalidValue;
 }
 
+// debugging aid (option `poison`): every byte of the activation workspace is set to 0xFF (NaN in every element type) before a
+// pass, so a layer that reads what this pass has not written -- padding channels, a halo outside its tensor, a buffer whose
+// producer has not finished -- turns the result into NaNs instead of silently reusing the previous pass's identical values
+int poison_arena(emd_engine* e, cudaStream_t s) {
+  if (tuning().poison && e->arena) CU(e, cudaMemsetAsync(e->arena, 0xFF, e->arena_bytes, s));
+  return EMD_OK;
+}
+
 int run_network_direct(emd_engine* e, const float* d_in, float* d_out, int n, int mode, cudaStream_t s) {
+  { int prc = poison_arena(e, s); if (prc) return prc; }
   ExecCtx c{e, mode == EMD_MODE_FP32 ? ET_F32 : (mode == EMD_MODE_BF16 ? ET_BF16 : ET_F16), n, s, d_in, d_out, {}};
   if (e->profile && e->events.size() < e->steps.size() + 1) {
     e->events.resize(e->steps.size() + 1);
@@ -758,6 +774,7 @@ int run_network_direct(emd_engine* e, const float* d_in, float* d_out, int n, in
 // h_in / h_out null = that side is already on the device (d_in / d_out used as given).
 int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const float* d_in, float* d_out, int n, int mode,
                        cudaStream_t s, bool first_pass) {
+  { int prc = poison_arena(e, s); if (prc) return prc; }
   ExecCtx c{e, mode == EMD_MODE_FP32 ? ET_F32 : (mode == EMD_MODE_BF16 ? ET_BF16 : ET_F16), n, s, d_in, d_out, {}};
   const size_t per = (size_t)e->S * e->S;
   const Tuning& tn = tuning();
@@ -931,6 +948,7 @@ int run_network(emd_engine* e, const float* d_in, float* d_out, int n, int mode,
     }
     cudaGraphDestroy(graph);
   }
+  { int prc = poison_arena(e, s); if (prc) return prc; }
   CU(e, cudaMemcpyAsync(e->g_in, d_in, bytes, cudaMemcpyDeviceToDevice, s));
   CU(e, cudaGraphLaunch(g.exec, s));
   CU(e, cudaMemcpyAsync(d_out, e->g_out, bytes, cudaMemcpyDeviceToDevice, s));
@@ -953,6 +971,7 @@ int grow(emd_engine* e, T** p, size_t* have, size_t need) {
   *p = nullptr; *have = 0;
   cudaError_t r = cudaMalloc(reinterpret_cast<void**>(p), need);
   if (r != cudaSuccess) return fail(e, EMD_ENOMEM, "cudaMalloc(%zu): %s", need, cudaGetErrorString(r));
+  if ((r = cudaMemset(*p, 0, need)) != cudaSuccess) return fail(e, EMD_ECUDA, "cudaMemset: %s", cudaGetErrorString(r));   // written once before any TMA access (plan_arena)
   *have = need;
   return EMD_OK;
 }
@@ -1553,6 +1572,7 @@ int emd_run_layer(emd_engine* e, const char* name, const float* in, const float*
   CU(e, cudaMalloc(&d_f32, n_stage * 4));
   CU(e, cudaMalloc(&d_in, n_in * 4));
   CU(e, cudaMalloc(&d_out, n_out * 4));
+  CU(e, cudaMemsetAsync(d_out, 0, n_out * 4, s));   // written once before any TMA access (plan_arena)
   CU(e, cudaMemcpyAsync(d_f32, in, n_in * 4, cudaMemcpyHostToDevice, s));
   CU(e, launch_cast(d_f32, d_in, n_in, ti.external ? ET_F32 : et, s));
   if (rres.t >= 0) {
@@ -1591,6 +1611,7 @@ long long emd_counter(const emd_engine* e, const char* name) {
   if (s == "launches") return e->cnt.launches;
   if (s == "tensor_core_launches") return e->cnt.umma;
   if (s == "graph_replays") return e->graph_replays;
+  if (s == "workspace_bytes") return (long long)e->arena_bytes;
   for (auto& k : kinds) if (s == k.n) return e->cnt.kind[k.k];
   return -1;
 }

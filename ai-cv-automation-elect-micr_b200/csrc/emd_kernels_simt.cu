@@ -540,6 +540,7 @@ __global__ void __launch_bounds__(128) dw_reg_kernel(const DwParams p, int nchun
 #pragma unroll
   for (int i = 0; i < kLW; ++i) x_ok |= (uint32_t)(x0 - 1 + i >= 0 && x0 - 1 + i < W) << i;
   const int ncol = min(kCW, W - x0);
+  const uint32_t upitch = (uint32_t)ipitch, uopitch = (uint32_t)opitch;
   const long long irs = (long long)W * ipitch, ors = (long long)p.OW * opitch;
   // running pointers: halo row 0 = image row y0 - 1, halo column 0 = image column x0 - 1 (never dereferenced outside the image)
   const uint32_t* pin = gin + (((long long)n * H + (y0 - 1)) * W + (x0 - 1)) * ipitch + cw;
@@ -549,7 +550,7 @@ __global__ void __launch_bounds__(128) dw_reg_kernel(const DwParams p, int nchun
   auto load_row = [&](int slot) {
     const uint32_t m = (yl >= 0 && yl < H) ? x_ok : 0u;
 #pragma unroll
-    for (int i = 0; i < kLW; ++i) raw[slot][i] = ((m >> i) & 1u) ? __ldg(pin + (long long)i * ipitch) : 0u;
+    for (int i = 0; i < kLW; ++i) raw[slot][i] = ((m >> i) & 1u) ? __ldg(pin + (uint32_t)i * upitch) : 0u;   // 32-bit offsets: one IMAD.WIDE.U32 per address
     pin += irs;
     ++yl;
   };
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(128) dw_reg_kernel(const DwParams p, int nchun
     if (j >= 2) {
 #pragma unroll
       for (int i = 0; i < kCW; ++i)
-        if (i < ncol) pout[(long long)i * opitch] = pack2<T>(acc[(j - 2) % 3][i].x, acc[(j - 2) % 3][i].y);
+        if (i < ncol) pout[(uint32_t)i * uopitch] = pack2<T>(acc[(j - 2) % 3][i].x, acc[(j - 2) % 3][i].y);
       pout += ors;
     }
   }

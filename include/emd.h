@@ -143,14 +143,15 @@ int emd_run_layer(emd_engine* e, const char* name, const float* in, const float*
 /* number of kernels this engine has launched since creation; of those, tcgen05 (UMMA) kernels */
 long long emd_kernel_launches(const emd_engine* e);
 long long emd_tensor_core_launches(const emd_engine* e);
-/* other counters by name: "launches", "tensor_core_launches", "graph_replays", and conv launches by the kernel that ran them:
+/* other counters by name: "launches", "tensor_core_launches", "graph_replays", "workspace_bytes" (activation workspace as
+ * planned now), and conv launches by the kernel that ran them:
  * "conv_fused_pair" (emd_fused.cu, cta_group::2 CTA pairs), "conv_fused_taps", "conv_fused_dw" (depthwise computed inside the GEMM
  * kernel), "conv_tcgen05_gen1" (emd_umma.cu), "conv_cuda_core" (FP32 mode, or a 16-bit shape no tensor-core kernel supports),
  * "final_tcgen05", "final_cuda_core".  -1 = unknown name.  The parity tests assert with these that the kernel under test ran. */
 long long emd_counter(const emd_engine* e, const char* name);
 /* Tuning / A-B switches (csrc/emd_kernels.h, struct Tuning): process-wide, initialised once from the EMD_* environment, changed
  * by name here; `e` (may be NULL) drops its captured graphs so the change takes effect.  Names: umma, fused, tma, pair,
- * final_umma, pdl, graphs, sliced_io, halves, mid_graph, pad_pitch, dw_cols, dw_reg, dw_reg_all, dw_tile, dw_strip, skip_taps, strict, graph_max_n, pair_min_rows, pair_min_items,
+ * final_umma, pdl, graphs, sliced_io, halves, mid_graph, pad_pitch, poison, dw_cols, dw_reg, dw_reg_all, dw_tile, dw_strip, skip_taps, strict, graph_max_n, pair_min_rows, pair_min_items,
  * io_slices, io_parts, dw_stages, dw_sa, dw_sb, dw_sh, dw_ring.  strict = 1: a GEMM-class layer of a 16-bit mode that no tensor-core
  * kernel supports is an error (EMD_ESTATE) instead of a silent CUDA-core launch. */
 int       emd_set_option(emd_engine* e, const char* name, long long value);

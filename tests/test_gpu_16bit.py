@@ -231,3 +231,103 @@ def test_full_size_batch_properties(emd):
     cc = eng.forward(crops[:2], mode="fp16")
     eng.set_tensor_cores(True)
     assert rel_l2(a[:2], cc) <= TOL_16BIT
+
+
+@pytest.mark.parametrize("crop", [96, 160])
+def test_depthwise_kernel_variants_bit_identical_small_maps(emd, crop):
+    """The stand-alone depthwise 3x3 of maps that do not tile into 8 x 16 pixel blocks has four kernels: register strips (default;
+    6- or 8-column strips; 160x160 crops give 40 / 20 / 10 pixel maps: 8-column strips, ragged last strips, several row blocks), shared-memory tiles, one-column strips and
+    one thread per pixel.  Same tap order everywhere: the layer outputs must be bit-identical, and within the contract of the
+    FP64 oracle."""
+    from oracle.weights import make_w1
+    rng = np.random.default_rng(100 + crop)
+    crops = rng.random((3 if crop < 128 else 2, crop, crop)).astype(np.float32)
+    w1 = make_w1(crops, seed=11)
+    eng = emd.Engine(cropsize=crop, max_batch=3)
+    eng.load_weights(emd.weights.pack(w1))
+    _, acts = oracle_acts(w1, crops)
+    table = layer_io_table()
+    variants = [("dw_reg", {}), ("dw_tile", {"dw_reg": 0}), ("dw_strip", {"dw_reg": 0, "dw_tile": 0}),
+                ("per pixel", {"dw_reg": 0, "dw_tile": 0, "dw_strip": 0})]
+    try:
+        for layer in ("cnn2", "cnn2_last", "cnn3", "cnn3_last", "cnn4_1", "mid3_0", "mid7_2", "deconv2_0", "deconv2_1"):
+            i, r, o = table[layer]
+            res = None if r is None else acts[r]
+            outs = []
+            for name, opts in variants:
+                for k, v in opts.items():
+                    eng.set_option(k, v)
+                outs.append(eng.run_layer(layer, acts[i], res, mode="fp16"))
+                for k in opts:
+                    eng.set_option(k, 1)
+            for (name, _), got in zip(variants[1:], outs[1:]):
+                assert np.array_equal(outs[0], got), (crop, layer, name, rel_l2(outs[0], got))
+            assert rel_l2(outs[0], acts[o]) <= TOL_16BIT, (crop, layer, rel_l2(outs[0], acts[o]))
+    finally:
+        for k in ("dw_reg", "dw_tile", "dw_strip"):
+            eng.set_option(k, 1)
+
+
+def test_depthwise_register_strips_match_tma_kernel_on_tiled_maps(emd):
+    """On maps that DO tile (32^2 and 64^2 maps of 728 / 256 channels at the benchmark crop size: the blocks with three N tiles) the TMA-fed depthwise
+    kernel is the default and the register-strip kernel an option (`dw_reg_all`): bit-identical layer outputs, random inputs."""
+    eng = emd.Engine(cropsize=512, max_batch=2)
+    eng.load_weights(emd.weights.pack(emd.weights.init_reference_weights(3)))
+    rng = np.random.default_rng(5)
+    try:
+        for layer, shape in (("mid5_1", (2, 32, 32, 728)), ("cnn3_last", (2, 64, 64, 728)), ("cnn3", (2, 64, 64, 256))):
+            x = (rng.random(shape, dtype=np.float32) * 2).astype(np.float32)
+            a = eng.run_layer(layer, x, None, mode="fp16")
+            eng.set_option("dw_reg_all", 1)
+            b = eng.run_layer(layer, x, None, mode="fp16")
+            eng.set_option("dw_reg_all", 0)
+            assert np.isfinite(a).all() and np.array_equal(a, b), (layer, rel_l2(a, b))
+    finally:
+        eng.set_option("dw_reg_all", 0)
+
+
+def test_no_layer_reads_what_the_pass_has_not_written(emd):
+    """Option `poison`: the whole activation workspace is filled with NaNs before every pass.  A layer that read padding channels
+    of the 768-pitch trunk tensors, a halo outside its tensor, or a tile whose producer had not finished would turn the output
+    into NaNs; identical passes normally hide such reads behind the previous pass's identical values.  Host (sliced, copy-
+    overlapped), device (direct, then graph replay) and half-batch passes, FP16 and FP32; results bit-identical to clean passes."""
+    import torch
+    rng = np.random.default_rng(3)
+    crops = rng.random((16, 512, 512)).astype(np.float32)
+    eng = emd.Engine(cropsize=512, max_batch=16)
+    eng.load_weights(emd.weights.pack(emd.weights.init_reference_weights(1)))
+    a = eng.forward(crops, mode="fp16")
+    f = eng.forward(crops[:2], mode="fp32")
+    try:
+        eng.set_option("poison", 1)
+        x = torch.from_numpy(crops).cuda()
+        outs = [eng.forward(crops, mode="fp16")]
+        for _ in range(3):                                   # direct, direct, graph replay
+            o = eng.forward(x, mode="fp16")
+            torch.cuda.synchronize()
+            outs.append(o.cpu().numpy())
+        for o in outs:
+            assert not np.isnan(o).any()
+            np.testing.assert_array_equal(o, a)
+        np.testing.assert_array_equal(eng.forward(crops[:8], mode="fp16"), a[:8])
+        np.testing.assert_array_equal(eng.forward(crops[:2], mode="fp32"), f)
+    finally:
+        eng.set_option("poison", 0)
+
+
+def test_first_pass_over_a_fresh_large_workspace(emd):
+    """Regression: the first pass over a newly allocated workspace of >= 28 GB (keep mode at max_batch 16: every activation in its
+    own buffer) intermittently faulted or returned wrong tiles until the workspace was cleared once after allocation
+    (plan_arena).  Five fresh engines, first keep pass each, bit-identical to the arena-planned pass."""
+    rng = np.random.default_rng(99)
+    crops = rng.random((8, 512, 512)).astype(np.float32)
+    blob = emd.weights.pack(emd.weights.init_reference_weights(1))
+    for it in range(5):
+        eng = emd.Engine(cropsize=512, max_batch=16)
+        eng.load_weights(blob)
+        a = eng.forward(crops, mode="fp16")
+        eng.set_keep_activations(True)
+        assert eng.counter("workspace_bytes") > 25e9
+        k = eng.forward(crops, mode="fp16")
+        np.testing.assert_array_equal(k, a)
+        eng.close()

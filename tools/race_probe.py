@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Find the first activation that differs between repeated identical device-buffer passes (intermittent-race hunt).
-  python tools/race_probe.py [iters] [keep(0/1)]"""
+"""Find the first activation that differs between repeated identical passes (intermittent-race hunt).
+  python tools/race_probe.py [iters] [keep(0/1)] [poison(0/1)] [host(0/1)] [batch]
+poison = 1 fills the workspace with NaNs before every pass (option `poison`): a layer that reads a tile its producer has not
+written yet then shows up as NaNs instead of silently reusing the previous pass's identical values."""
 import importlib
 import os
 import sys
@@ -12,9 +14,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 emd = importlib.import_module("ai-cv-automation-elect-micr_b200")
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 keep = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+poison = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+host = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+NB = int(sys.argv[5]) if len(sys.argv) > 5 else 16
+MODE = os.environ.get("PROBE_MODE", "fp16")
 rng = np.random.default_rng(99)
-crops = rng.random((16, 512, 512)).astype(np.float32)
-eng = emd.Engine(cropsize=512, max_batch=16)
+crops = rng.random((NB, 512, 512)).astype(np.float32)
+eng = emd.Engine(cropsize=512, max_batch=NB)
 eng.load_weights(emd.weights.pack(emd.weights.init_reference_weights(1)))
 names = []
 for i in range(4):
@@ -24,23 +30,39 @@ for b in range(11):
     names += [f"mid{b}_0", f"mid{b}_1", f"trunk_mid{b}"]
 names += ["aspp_1x1", "aspp_r6", "aspp_r12", "aspp_r18", "aspp_image", "aspp_pellet", "upsample4", "deconv2_0", "residual2_d", "dec2",
           "deconv2to1", "deconv1_0", "residual1_d", "dec1", "deconv1to0", "deconv0_0", "residual0_d", "dec0"]
-x = torch.from_numpy(crops).cuda()
+x = crops if host else torch.from_numpy(crops).cuda()
 torch.cuda.synchronize()
+
+
+def run():
+    o = eng.forward(x, mode=MODE)
+    torch.cuda.synchronize()
+    return o if host else o.cpu().numpy()
+
+
+out0 = run()          # reference: arena-planned pass, no poison
 if keep:
     eng.set_keep_activations(True)
-out0 = eng.forward(x, mode="bf16"); torch.cuda.synchronize()
-out0 = out0.cpu().numpy()
+    for _ in range(2):    # the second pass runs over the first one's (identical) values: a read-before-write race is masked in it
+        eng.forward(x, mode=MODE); torch.cuda.synchronize()
 A = {n: eng.activation(n).copy() for n in names} if keep else {}
+if poison:
+    eng.set_option("poison", 1)
+nbad = 0
 for it in range(iters):
-    o = eng.forward(x, mode="bf16"); torch.cuda.synchronize()
-    o = o.cpu().numpy()
-    per = [int((o[i] != out0[i]).sum()) for i in range(16)]
-    print("iter", it, "output mismatches per crop", per if any(per) else "none")
+    o = run()
+    per = [int((o[i] != out0[i]).sum()) + int(np.isnan(o[i]).sum()) for i in range(NB)]
+    nbad += any(per)
+    if any(per) or it == iters - 1:
+        print("iter", it, "output mismatches per crop", per if any(per) else "none", "| bad passes so far", nbad, flush=True)
     if keep and any(per):
         for n in names:
             b = eng.activation(n)
             m = (b != A[n])
             if m.any():
-                imgs = sorted(set(np.nonzero(m.reshape(16, -1).any(axis=1))[0].tolist()))
-                print("   first differing activation:", n, "elements", int(m.sum()), "crops", imgs, "max abs", float(np.abs(b.astype(np.float64) - A[n]).max()))
+                imgs = sorted(set(np.nonzero(m.reshape(NB, -1).any(axis=1))[0].tolist()))
+                yy, xx = np.nonzero(m[imgs[0]].any(axis=-1))
+                print("   first differing activation:", n, b.shape, "elements", int(m.sum()), "NaNs", int(np.isnan(b).sum()), "crops", imgs,
+                      "rows", int(yy.min()), int(yy.max()), "cols", int(xx.min()), int(xx.max()),
+                      "channels", sorted(set(np.nonzero(m[imgs[0]].any(axis=(0, 1)))[0].tolist()))[:6], flush=True)
                 break
