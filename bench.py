@@ -214,13 +214,13 @@ def run_reference(args, rank, world):
     sample = (f"{done} batch-1 passes over one {CROP}x{CROP} crop of the workload's batch per timed step: the reference runs one "
               f"sess.run per crop (DEN:646-647), so its crops/s does not depend on the batch; PyTorch-CPU restatement of the "
               f"reference TF graph (TensorFlow is not installable here), FP32")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / done, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(n_input_sets()),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def sha(arrays):
@@ -230,7 +230,27 @@ def sha(arrays):
     return h.hexdigest()
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner from C on the
+    first collective), so file descriptor 1 points at stderr for the whole run and the line goes to a duplicate of the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -525,7 +545,7 @@ def main():
             line["configs"] = configs
         if stream_cfg:
             line["stream_4096"] = stream_cfg
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
