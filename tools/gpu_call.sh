@@ -1,7 +1,8 @@
 #!/bin/bash
+# scratch driver of the current GPU call (rewritten per call; the reusable pieces are gpu_validate.sh and gpu_ab.sh)
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r2ad_bench_8gpu.json 2> gpurun_out/r2ad_bench_8gpu.err; echo "8gpu rc=$?"
-cut -c1-300 gpurun_out/r2ad_bench_8gpu.json
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 8 --steps 3 --warmup 1 > gpurun_out/r2ad_bench_8gpu_ref.json 2> gpurun_out/r2ad_bench_8gpu_ref.err; echo "8gpu ref rc=$?"
-cut -c1-200 gpurun_out/r2ad_bench_8gpu_ref.json
+timeout 120 python tools/run_layer.py --layer deconv0_0 --n 8 --mode fp16 > gpurun_out/r2ae_plain.log 2>&1; echo "plain rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_conv_kernel -s 1 -c 1 -f -o gpurun_out/r2ae_d00 python tools/run_layer.py --layer deconv0_0 --n 8 --mode fp16 > gpurun_out/r2ae_ncu_d00.log 2>&1; echo "ncu d00 rc=$?"
+timeout 120 python tools/run_layer.py --layer mid5_1 --crop 96 --n 1024 --mode fp16 > gpurun_out/r2ae_plain96.log 2>&1; echo "plain96 rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:dw_reg_kernel -s 1 -c 1 -f -o gpurun_out/r2ae_dwreg python tools/run_layer.py --layer mid5_1 --crop 96 --n 1024 --mode fp16 > gpurun_out/r2ae_ncu_dwreg.log 2>&1; echo "ncu dwreg rc=$?"
