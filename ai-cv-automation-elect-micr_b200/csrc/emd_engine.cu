@@ -117,6 +117,12 @@ struct emd_engine {
   std::vector<cudaEvent_t> events;
   // CUDA graphs of whole passes for small batches
   std::map<int, GraphSlot> graphs;
+  // forked pairs (option fork_sms): fork_side[i] = j when step j (a 1x1 conv) reads the same tensor as the separable block whose
+  // GEMM step is i and may run beside it on the other stream, each kernel on its share of the SMs
+  std::vector<int> fork_side;
+  cudaStream_t fork_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int fork_skip = -1;
   std::map<int, GraphSlot> mid_graphs;   // whole-batch middle section of the host-buffer pass (run_network_sliced)
   float *g_in = nullptr, *g_out = nullptr;
   long long graph_replays = 0;
@@ -382,6 +388,13 @@ int plan_arena(emd_engine* e) {
       if (t.last >= e->tail_start) { t.first = std::min(t.first, e->tail_start); t.last = nsteps - 1; }
     }
   }
+  // forked pairs: the side conv runs WHILE the block before it runs, so its output must not share memory with anything that
+  // block (or its depthwise step) still uses
+  for (int i = 0; i < (int)e->fork_side.size(); ++i)
+    if (e->fork_side[i] >= 0) {
+      Tensor& t = e->tensors[e->steps[e->fork_side[i]].out.t];
+      if (t.last >= 0) t.first = std::min(t.first, i - 1);
+    }
   std::vector<int> order;
   for (int i = 0; i < (int)e->tensors.size(); ++i) {
     Tensor& t = e->tensors[i];
@@ -532,7 +545,11 @@ struct ExecCtx {
   float* d_out;       // network output (device, f32)
   std::vector<Override> ov;
   int b0 = 0;         // first crop of the batch this step works on (a slice of the batch: every view starts b0 images in)
+  int sms = 0;        // > 0: this launch may use only that many SMs (a forked pair of kernels shares the GPU); 0 = all
+  bool fork_ok = false;   // whole-network passes only: a step may launch its forked partner (run_step)
 };
+
+inline int sms_of(const ExecCtx& c) { return c.sms > 0 ? c.sms : c.e->num_sms; }
 
 View make_view(const ExecCtx& c, Ref r) {
   const Tensor& t = c.e->tensors[r.t];
@@ -554,16 +571,16 @@ cudaError_t run_conv(ExecCtx& c, ConvParams& p, const Step& s) {
   auto tc = [&](int kind, cudaError_t r) { e->cnt.umma++; e->cnt.kind[kind]++; return r; };
   if (c.et != ET_F32 && e->use_umma && final_tma_supported(p, c.et)) {
     p.w = s.wr[c.et];
-    if (final_umma_supported(p, c.et)) return tc(LK_FINAL_UMMA, launch_final_umma(p, s.scale0, s.shift0, c.et, e->num_sms, c.s));
+    if (final_umma_supported(p, c.et)) return tc(LK_FINAL_UMMA, launch_final_umma(p, s.scale0, s.shift0, c.et, sms_of(c), c.s));
     e->cnt.kind[LK_FINAL_TMA]++;
-    return launch_final_tma(p, s.scale0, s.shift0, c.et, e->num_sms, c.s);
+    return launch_final_tma(p, s.scale0, s.shift0, c.et, sms_of(c), c.s);
   }
   if (c.et != ET_F32 && e->use_umma && s.w16[c.et] && fused_supported(p, c.et, nullptr)) {
-    const cudaError_t r = launch_conv_fused(p, c.et, nullptr, e->num_sms, c.s);
+    const cudaError_t r = launch_conv_fused(p, c.et, nullptr, sms_of(c), c.s);
     return tc(last_launch_kind(), r);
   }
   if (c.et != ET_F32 && e->use_umma && s.w16[c.et] && umma_supported(p, c.et))
-    return tc(LK_UMMA_GEN1, launch_conv_umma(p, c.et, e->num_sms, c.s));
+    return tc(LK_UMMA_GEN1, launch_conv_umma(p, c.et, sms_of(c), c.s));
   if (c.et != ET_F32 && e->use_umma && tuning().strict) {   // a silent CUDA-core fallback would pass every test and cost 10x
     e->err = "strict: no tensor-core kernel supports step " + s.name;
     return cudaErrorNotSupported;
@@ -622,13 +639,51 @@ int step_error(emd_engine* e, int idx, cudaError_t r) {
 }
 
 cudaError_t run_step_impl(ExecCtx& c, int idx);
+// A separable block whose depthwise runs inside its GEMM kernel is bound by that kernel's math warps and leaves a third of the
+// HBM bandwidth unused; the 1x1 conv that follows it in the decoder (residualN_d) reads the same tensor and is bound by HBM alone.
+// With fork_sms = n the two run side by side: the block on num_sms - n SMs of the pass's stream, the 1x1 conv on n SMs of a
+// second stream, joined before the next step (which adds the two).
+static int fork_side_of(const ExecCtx& c, int idx) {
+  emd_engine* e = c.e;
+  const int n = tuning().fork_sms;
+  if (!c.fork_ok || n < 8 || n > e->num_sms - 32 || e->profile || c.et == ET_F32 || !e->use_umma || c.sms || !e->fork_stream) return -1;
+  if (idx >= (int)e->fork_side.size() || e->fork_side[idx] < 0) return -1;
+  if (!dw_fusable(c, idx, nullptr)) return -1;
+  return e->fork_side[idx];
+}
+
 cudaError_t run_step(ExecCtx& c, int idx) {
-  Step& s = c.e->steps[idx];
-  const long long before = c.e->cnt.launches;
+  emd_engine* e = c.e;
+  Step& s = e->steps[idx];
+  if (e->fork_skip == idx) { e->fork_skip = -1; return cudaSuccess; }   // ran beside the step before it
+  const long long before = e->cnt.launches;
   s.fused = false;
-  cudaError_t r = run_step_impl(c, idx);
-  s.nlaunch = (int)(c.e->cnt.launches - before);
-  return r;
+  const int side = fork_side_of(c, idx);
+  if (side < 0) {
+    cudaError_t r = run_step_impl(c, idx);
+    s.nlaunch = (int)(e->cnt.launches - before);
+    return r;
+  }
+  cudaError_t r = cudaEventRecord(e->ev_fork, c.s);                     // everything both kernels read is complete here
+  if (r != cudaSuccess) return r;
+  c.sms = e->num_sms - tuning().fork_sms;
+  r = run_step_impl(c, idx);
+  c.sms = 0;
+  s.nlaunch = (int)(e->cnt.launches - before);
+  if (r != cudaSuccess) return r;
+  if ((r = cudaStreamWaitEvent(e->fork_stream, e->ev_fork, 0)) != cudaSuccess) return r;
+  ExecCtx c2 = c;
+  c2.s = e->fork_stream; c2.sms = tuning().fork_sms;
+  Step& s2 = e->steps[side];
+  const long long before2 = e->cnt.launches;
+  s2.fused = false;
+  r = run_step_impl(c2, side);
+  s2.nlaunch = (int)(e->cnt.launches - before2);
+  if (r != cudaSuccess) return r;
+  if ((r = cudaEventRecord(e->ev_join, e->fork_stream)) != cudaSuccess) return r;
+  if ((r = cudaStreamWaitEvent(c.s, e->ev_join, 0)) != cudaSuccess) return r;
+  e->fork_skip = side;
+  return cudaSuccess;
 }
 
 cudaError_t run_step_impl(ExecCtx& c, int idx) {
@@ -647,8 +702,8 @@ cudaError_t run_step_impl(ExecCtx& c, int idx) {
       p.w = s.dw; p.in_f32 = ti.external;
       e->cnt.launches++;
       if (tuning().dw_reg_all && dw_reg_supported(p, c.et)) return launch_dw_reg(p, c.et, c.s);
-      if (e->use_umma && dw_tma_supported(p, c.et)) return launch_dw_tma(p, c.et, e->num_sms, c.s);
-      if (e->use_umma && dw_s2_tma_supported(p, c.et)) return launch_dw_s2_tma(p, c.et, e->num_sms, c.s);
+      if (e->use_umma && dw_tma_supported(p, c.et)) return launch_dw_tma(p, c.et, sms_of(c), c.s);
+      if (e->use_umma && dw_s2_tma_supported(p, c.et)) return launch_dw_s2_tma(p, c.et, sms_of(c), c.s);
       if (tuning().dw_reg && dw_reg_supported(p, c.et)) return launch_dw_reg(p, c.et, c.s);
       if (tuning().dw_tile && dw_tile_supported(p, c.et)) return launch_dw_tile(p, c.et, c.s);
       if (tuning().dw_strip && dw_strip_supported(p, c.et)) return launch_dw_strip(p, c.et, c.s);
@@ -689,7 +744,7 @@ cudaError_t run_step_impl(ExecCtx& c, int idx) {
         e->cnt.launches++;
         e->cnt.umma++;
         e->cnt.kind[LK_FUSED_DW]++;
-        return launch_conv_fused(p, c.et, e->steps[idx - 1].dw, e->num_sms, c.s);
+        return launch_conv_fused(p, c.et, e->steps[idx - 1].dw, sms_of(c), c.s);
       }
       p = ConvParams{};
       conv_params(c, s, p);
@@ -722,7 +777,7 @@ cudaError_t run_step_impl(ExecCtx& c, int idx) {
       if (c.et != ET_F32 && e->use_umma && s.w16[c.et] && fused_multi_supported(ph, 4, c.et)) {
         e->cnt.launches++;
         e->cnt.umma++;
-        const cudaError_t r = launch_conv_fused_multi(ph, 4, c.et, e->num_sms, c.s);   // one launch: work items = (input tile, phase)
+        const cudaError_t r = launch_conv_fused_multi(ph, 4, c.et, sms_of(c), c.s);   // one launch: work items = (input tile, phase)
         e->cnt.kind[last_launch_kind()]++;
         return r;
       }
@@ -747,6 +802,7 @@ int poison_arena(emd_engine* e, cudaStream_t s) {
 int run_network_direct(emd_engine* e, const float* d_in, float* d_out, int n, int mode, cudaStream_t s) {
   { int prc = poison_arena(e, s); if (prc) return prc; }
   ExecCtx c{e, mode == EMD_MODE_FP32 ? ET_F32 : (mode == EMD_MODE_BF16 ? ET_BF16 : ET_F16), n, s, d_in, d_out, {}};
+  c.fork_ok = true; e->fork_skip = -1;
   if (e->profile && e->events.size() < e->steps.size() + 1) {
     e->events.resize(e->steps.size() + 1);
     for (auto& ev : e->events) CU(e, cudaEventCreate(&ev));
@@ -776,6 +832,7 @@ int run_network_sliced(emd_engine* e, const float* h_in, float* h_out, const flo
                        cudaStream_t s, bool first_pass) {
   { int prc = poison_arena(e, s); if (prc) return prc; }
   ExecCtx c{e, mode == EMD_MODE_FP32 ? ET_F32 : (mode == EMD_MODE_BF16 ? ET_BF16 : ET_F16), n, s, d_in, d_out, {}};
+  c.fork_ok = true; e->fork_skip = -1;
   const size_t per = (size_t)e->S * e->S;
   const Tuning& tn = tuning();
   const int k_env = tn.io_slices;
@@ -1021,8 +1078,19 @@ int emd_create(emd_engine** out, int device, int cropsize, int variant, int max_
   }
   e->num_sms = prop.multiProcessorCount;
   CUC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithFlags(&e->fork_stream, cudaStreamNonBlocking));
+  CUC(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  CUC(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   build_schedule(e);
   annotate_work(e);
+  // forked pairs: [i-1] depthwise step, [i] its GEMM step, [i+1] a 1x1 conv without residual operand on the same input tensor
+  e->fork_side.assign(e->steps.size(), -1);
+  for (int i = 1; i + 1 < (int)e->steps.size(); ++i) {
+    const Step &d = e->steps[i - 1], &m = e->steps[i], &sd = e->steps[i + 1];
+    if (d.kind == SK_DW && m.kind == SK_CONV && d.layer == m.layer && m.res.t < 0 && sd.kind == SK_CONV && sd.k == 1 && sd.stride == 1 &&
+        sd.res.t < 0 && sd.in.t == d.in.t && sd.out.t != m.out.t && sd.out.t != d.in.t && !e->tensors[sd.out.t].external)
+      e->fork_side[i] = i + 1;
+  }
   int rc = plan_arena(e);
   if (rc != EMD_OK) { g_create_error = e->err; emd_destroy(e); return rc; }
   const size_t io = (size_t)max_batch * cropsize * cropsize * sizeof(float);
@@ -1061,6 +1129,9 @@ int emd_destroy(emd_engine* e) {
     for (int i = 0; i < emd_engine::kSlices; ++i) { cudaEventDestroy(e->ev_sl_in[i]); cudaEventDestroy(e->ev_sl_fin[i]); }
     cudaEventDestroy(e->ev_in_free); cudaEventDestroy(e->ev_out_free);
   }
+  if (e->fork_stream) cudaStreamDestroy(e->fork_stream);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return EMD_OK;

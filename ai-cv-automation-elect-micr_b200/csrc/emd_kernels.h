@@ -158,6 +158,7 @@ struct Tuning {
   int dw_strip = 1;        // EMD_DISABLE_DW_STRIP: small-map / dilated depthwise on the one-thread-per-pixel kernel
   int dw_cols = 1;         // EMD_DISABLE_DW_COLS: depthwise producer with one pixel column per thread (first form)
   int pad_pitch = 1;       // EMD_DISABLE_PAD_PITCH: 728-channel tensors dense (1456-byte pixels) instead of padded to 768 channels (read at emd_create)
+  int fork_sms = 0;        // EMD_FORK_SMS=n: the decoder's 1x1 residual convs run beside the separable block that reads the same tensor, on n SMs of a second stream (0 = one kernel at a time)
   int poison = 0;          // EMD_POISON=1 (debugging): the activation workspace is filled with NaNs before every pass
   int strict = 0;          // EMD_STRICT=1: a GEMM-class layer of a 16-bit mode that would run on the CUDA-core kernel is an error
   int graph_max_n = 32;    // EMD_GRAPH_MAX_N: largest batch replayed from a graph

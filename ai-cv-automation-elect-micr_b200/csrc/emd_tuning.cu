@@ -27,6 +27,7 @@ const Entry kTable[] = {
     {"dw_strip", "EMD_DISABLE_DW_STRIP", &Tuning::dw_strip, true},
     {"dw_cols", "EMD_DISABLE_DW_COLS", &Tuning::dw_cols, true},
     {"pad_pitch", "EMD_DISABLE_PAD_PITCH", &Tuning::pad_pitch, true},
+    {"fork_sms", "EMD_FORK_SMS", &Tuning::fork_sms, false},
     {"poison", "EMD_POISON", &Tuning::poison, false},
     {"strict", "EMD_STRICT", &Tuning::strict, false},
     {"graph_max_n", "EMD_GRAPH_MAX_N", &Tuning::graph_max_n, false},

@@ -331,3 +331,33 @@ def test_first_pass_over_a_fresh_large_workspace(emd):
         k = eng.forward(crops, mode="fp16")
         np.testing.assert_array_equal(k, a)
         eng.close()
+
+
+def test_forked_side_convs_bit_identical(emd):
+    """Option `fork_sms`: the decoder's 1x1 residual convs run beside the separable block that reads the same tensor, on their own
+    share of the SMs and a second stream.  Same kernels, same arithmetic: bit-identical outputs for host (sliced, half-batch
+    tail), device (direct, then graph replay) and small-batch passes, also over a NaN-poisoned workspace (an ordering mistake
+    between the two streams would read unwritten data)."""
+    import torch
+    rng = np.random.default_rng(8)
+    crops = rng.random((16, 512, 512)).astype(np.float32)
+    eng = emd.Engine(cropsize=512, max_batch=16)
+    eng.load_weights(emd.weights.pack(emd.weights.init_reference_weights(2)))
+    a = eng.forward(crops, mode="fp16")
+    x = torch.from_numpy(crops).cuda()
+    try:
+        eng.set_option("fork_sms", 48)
+        eng.set_option("poison", 1)
+        np.testing.assert_array_equal(eng.forward(crops, mode="fp16"), a)
+        for _ in range(3):
+            o = eng.forward(x, mode="fp16")
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(o.cpu().numpy(), a)
+        np.testing.assert_array_equal(eng.forward(crops[:3], mode="fp16"), a[:3])
+        eng.set_option("poison", 0)
+        ob = eng.forward(x, mode="bf16")
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(eng.forward(crops, mode="bf16"), ob.cpu().numpy())
+    finally:
+        eng.set_option("fork_sms", 0)
+        eng.set_option("poison", 0)
