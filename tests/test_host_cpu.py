@@ -180,3 +180,30 @@ def test_preprocess_crop_values_match_the_reference_order(emd):
     assert got[0, 10, 20, 0] == 1.0 and (np.delete(got.ravel(), 10 * 64 + 20) == 0.0).all()
     const = np.full((32, 48), 7.0, np.float32)
     assert (den.preprocess_crop(const, 64) == 0.5).all()
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py's contract: ONE JSON line on stdout (everything else -- NCCL's banner, progress -- goes to stderr); the reference
+    arm times the CPU port and needs no GPU.  One step, no warm-up: a few seconds."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "denoised 512x512 crops/s" and d["unit"] == "crops/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("batch 32 of 512x512")
+
+
+def test_bench_reference_arm_other_ranks_exit_quietly():
+    """Under torchrun only rank 0 runs the reference arm; the other ranks exit 0 without work or output."""
+    import subprocess
+    import sys
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
