@@ -1028,7 +1028,10 @@ int grow(emd_engine* e, T** p, size_t* have, size_t need) {
   *p = nullptr; *have = 0;
   cudaError_t r = cudaMalloc(reinterpret_cast<void**>(p), need);
   if (r != cudaSuccess) return fail(e, EMD_ENOMEM, "cudaMalloc(%zu): %s", need, cudaGetErrorString(r));
-  if ((r = cudaMemset(*p, 0, need)) != cudaSuccess) return fail(e, EMD_ECUDA, "cudaMemset: %s", cudaGetErrorString(r));   // written once before any TMA access (plan_arena)
+  // written once before any TMA access (plan_arena); the memset runs on the legacy stream, which the engine's non-blocking
+  // streams do not wait for: finish it here (allocation is rare)
+  if ((r = cudaMemset(*p, 0, need)) != cudaSuccess || (r = cudaDeviceSynchronize()) != cudaSuccess)
+    return fail(e, EMD_ECUDA, "clearing a new buffer: %s", cudaGetErrorString(r));
   *have = need;
   return EMD_OK;
 }

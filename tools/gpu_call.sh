@@ -2,5 +2,5 @@
 # scratch driver of the current GPU call (rewritten per call; the reusable pieces are gpu_validate.sh and gpu_ab.sh)
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/r2ai_bench_4gpu.json 2> gpurun_out/r2ai_bench_4gpu.err; echo "4gpu rc=$?"
-cut -c1-300 gpurun_out/r2ai_bench_4gpu.json
+timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > gpurun_out/r2aj_parity.log 2>&1; echo "parity rc=$?"; tail -2 gpurun_out/r2aj_parity.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2aj_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/r2aj_smoke.log
