@@ -403,6 +403,7 @@ int plan_arena(emd_engine* e) {
     // 128-byte load or store) straddles two 128-byte lines and starts on a half sector for odd pixels.  Laid out with a pitch of
     // 768 channels every chunk is one aligned line; the 40 padding channels are never read or written (the tensor maps and the
     // kernels see C = 728).  Only for tensors that are never addressed as channel slices (concat buffers keep their layout).
+    t.pitch = t.C;
     if (tuning().pad_pitch && t.C > 64 && (t.C & 63)) {
       bool sliced = false;
       for (const Step& st : e->steps)
