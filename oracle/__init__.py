@@ -13,5 +13,7 @@ The reference tree holds no golden vectors, known-answer tests or fixtures
 for this path.  The oracle therefore restates the
 published TF op semantics and is anchored on closed-form
 mini-cases, adjoint identities and the integer tile-plan goldens of
-SURVEY.md App. D -- not on outputs of the reference itself.
+SURVEY.md App. D -- not on outputs of the reference itself.  ``naive.py`` is a
+second, independently written restatement (plain numpy); the CPU suite checks
+that the two agree to rounding.
 """

@@ -209,3 +209,24 @@ def test_stitch_weights_are_reciprocal_counts():
 def test_image_smaller_than_crop_rejected():
     with pytest.raises(ValueError):
         W.tile_origins(511)
+
+
+@pytest.mark.parametrize("variant,size", [("A", 128), ("B", 64)])
+def test_second_independent_restatement_agrees(variant, size):
+    """oracle/naive.py is a second restatement of the reference graph in plain numpy float64, written op by op from the
+    definitions (explicit SAME padding and tap loops, sub-pixel closed form of the transposed conv, per-pixel legacy bilinear,
+    un-fused BatchNorm).  On calibrated weights (every layer O(1), so no branch hides behind another) the two restatements must
+    agree to rounding -- a transcription slip in either one (tap order, padding side, concat order, BN order, kernel layout,
+    a shifted transposed conv) is a difference of order one.  128 x 128 crops put in-bounds dilated taps on the 8 x 8 ASPP map."""
+    from oracle.naive import NaiveNet
+    from oracle.net import OracleNet
+    from oracle.weights import make_w1
+    rng = np.random.default_rng(31)
+    crops = rng.random((2, size, size)).astype(np.float32)
+    w1 = make_w1(crops, seed=9, variant=variant)
+    ref = OracleNet(w1, size, variant=variant, dtype=torch.float64).forward(crops)
+    got = NaiveNet(w1, size, variant=variant).forward(crops)
+    assert ref.shape == got.shape == (2, size, size)
+    assert float(np.abs(ref).max()) > 1e-2 and float((ref > 0).mean()) > 0.05      # a live output, not an all-zero clip
+    err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+    assert err <= 1e-10, err
